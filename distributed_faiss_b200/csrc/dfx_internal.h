@@ -1,0 +1,85 @@
+// dfx_internal.h -- index object + launcher declarations shared by the .cu files.
+#pragma once
+#include "dfx_common.cuh"
+#include <vector>
+#include <mutex>
+#include <memory>
+#include <algorithm>
+
+struct dfx_index {
+    dfx_cfg cfg{};
+    int M = 0, ksub = 0, dsub = 0;
+    int64_t nprobe = 1;  // faiss default (index.py:47 copies it back into cfg for knnlm)
+    bool trained = false;
+
+    // list-sorted storage ("sorted") and arrival-order staging ("pending")
+    int64_t n_sorted = 0, n_pending = 0;
+    DevBuf centroids, cnorm, codebooks;
+    DevBuf list_off;                    // int64[nlist+1]
+    std::vector<int64_t> h_list_off;    // host mirror
+    DevBuf ids;                         // int32[n_sorted] shard-local ids, list-sorted
+    DevBuf payload;                     // kind-specific rows, list-sorted (FLAT: arrival order)
+    DevBuf tvals;                       // IVF_PQ: f32[n_sorted]
+    DevBuf xnorm;                       // FLAT + L2: f32[n]
+    DevBuf p_list, p_payload, p_tvals;  // pending: int32 list per row, payload rows, tvals
+    int64_t p_cap = 0;
+    int64_t reserve_hint = 0;
+
+    // search workspace (grow-only)
+    DevBuf w_vals, w_keys, w_dis0, w_lut, w_part, w_q, w_D, w_I, w_misc;
+    // reconstruct support: inverse of ids (shard-local id -> storage position)
+    DevBuf inv;
+    bool inv_valid = false;
+    // training knobs (dfx_set_param)
+    int kmeans_niter = 25;            // faiss Clustering default niter
+    int max_points_per_centroid = 256;  // faiss Clustering default
+    uint64_t train_seed = 1234;       // faiss Clustering default seed
+
+    // last-search bookkeeping
+    int64_t last_nq = 0, last_nprobe = 0;
+    bool last_keys_valid = false;
+
+    cudaStream_t stream = nullptr;  // used by the host-pointer entry points
+    std::mutex mu;
+
+    size_t row_bytes() const {
+        switch (cfg.kind) {
+            case DFX_FLAT:
+            case DFX_IVF_FLAT: return (size_t)cfg.d * 4;
+            case DFX_IVF_PQ: return (size_t)M;
+            case DFX_IVF_SQ16: return (size_t)cfg.d * 2;
+        }
+        return 0;
+    }
+    int64_t ntotal() const { return n_sorted + n_pending; }
+    bool is_ivf() const { return cfg.kind != DFX_FLAT; }
+};
+
+// ---- dfx_search.cu
+// values[q][j] = ranking value of row (col0+j) of X for query q (IP: -q.x ; L2: |x|^2 - 2 q.x)
+void dfx_launch_gemm_values(const float* Q, int64_t nq, const float* X, const float* xnorm,
+                            int64_t ncols, int d, int metric, float* out, int64_t ld_out,
+                            cudaStream_t st);
+void dfx_launch_row_norms(const float* X, int64_t n, int d, float* out, cudaStream_t st);
+// top-k columns per row of a values matrix -> keys int32[nrows,k] (and optional values)
+void dfx_launch_select_cols(const float* vals, int64_t nrows, int n, int64_t ld, int k,
+                            uint32_t col_base, int32_t* keys, float* kvals, uint64_t* comp_out,
+                            int64_t comp_ld, cudaStream_t st);
+void dfx_search_impl(dfx_index* idx, int64_t nq, const float* d_x, int64_t k, float* d_D,
+                     int64_t* d_I, cudaStream_t st);
+void dfx_merge_impl(int64_t S, int64_t nq, int64_t k, const float* d_D, const int64_t* d_I,
+                    int negate, float* d_outD, int64_t* d_outI, cudaStream_t st);
+void dfx_map_ids_impl(int64_t n, const int64_t* d_ids, const int64_t* d_table, int64_t* d_out,
+                      cudaStream_t st);
+void dfx_stats_impl(dfx_index* idx, int64_t* ndis, cudaStream_t st);
+
+// ---- dfx_build.cu
+void dfx_train_impl(dfx_index* idx, int64_t n, const float* d_x, cudaStream_t st);
+void dfx_add_impl(dfx_index* idx, int64_t n, const float* d_x, cudaStream_t st);
+void dfx_finalize_impl(dfx_index* idx, cudaStream_t st);
+void dfx_reconstruct_impl(dfx_index* idx, int64_t n, const int64_t* d_ids, float* d_out,
+                          cudaStream_t st);
+void dfx_assign_impl(dfx_index* idx, const float* d_cent, const float* d_cnorm, int64_t nlist,
+                     int metric, int d, int64_t n, const float* d_x, int32_t* d_assign,
+                     cudaStream_t st);
+void dfx_compute_tvals_sorted(dfx_index* idx, cudaStream_t st);

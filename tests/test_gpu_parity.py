@@ -1,0 +1,278 @@
+"""GPU parity tests: the CUDA path (through the C-ABI, libdfx.so) against the CPU oracle.
+
+Bar (BASELINE.json north_star): returned ids bit-exact at full nprobe, distances within 1e-4.
+Because the kernels follow the oracle's canonical summation orders the distances are in fact
+required to be BIT-EXACT here (np.array_equal on float32); the 1e-4 tolerance is only used
+against the independent float64 restatement (oracle/ref_numpy.py).
+"""
+import numpy as np
+import pytest
+
+from tests.conftest import clustered
+
+pytestmark = pytest.mark.gpu
+
+IP, L2 = 0, 1
+
+
+def _engine():
+    from distributed_faiss_b200 import engine
+
+    return engine
+
+
+def _mk_pair(kind, d, metric, nlist=0, M=0):
+    """(gpu index, oracle index) of the same configuration"""
+    from oracle import oracle as O
+
+    E = _engine()
+    kinds = {"flat": E.KIND_FLAT, "ivf_flat": E.KIND_IVF_FLAT, "ivf_pq": E.KIND_IVF_PQ, "ivf_sq": E.KIND_IVF_SQ16}
+    g = E.GpuIndex(kinds[kind], d, metric, nlist=nlist, pq_m=M)
+    o = O.make_index(kind, d, metric=metric, nlist=nlist, M=M)
+    return g, o
+
+
+def _assert_same(Dg, Ig, Do, Io, what):
+    same_i = np.array_equal(Ig, Io)
+    same_d = np.array_equal(Dg, Do)
+    if not (same_i and same_d):
+        bad = np.argwhere((Ig != Io) | (Dg != Do))
+        q, j = bad[0]
+        raise AssertionError(
+            f"{what}: {len(bad)} mismatching slots of {Ig.size}; first at q={q} j={j}: "
+            f"gpu=({Dg[q, j]!r},{Ig[q, j]}) oracle=({Do[q, j]!r},{Io[q, j]})\n"
+            f"gpu row   D={Dg[q]} I={Ig[q]}\noracle row D={Do[q]} I={Io[q]}")
+
+
+# ------------------------------------------------------------------ flat
+@pytest.mark.parametrize("metric", [IP, L2])
+@pytest.mark.parametrize("nq", [1, 7, 33])
+def test_flat_matches_oracle(metric, nq):
+    rs = np.random.RandomState(1)
+    d, n, k = 128, 5000, 10
+    xb = rs.rand(n, d).astype(np.float32)
+    xq = rs.rand(nq, d).astype(np.float32)
+    g, o = _mk_pair("flat", d, metric)
+    g.add(xb[:3000]); g.add(xb[3000:])
+    o.add(xb)
+    assert g.ntotal == n
+    _assert_same(*g.search(xq, k), *o.search(xq, k), f"flat metric={metric}")
+
+
+def test_flat_config1_100k():
+    """BASELINE configs[0]: flat d=128, 100k vectors, 1k queries (oracle on a query sample)."""
+    rs = np.random.RandomState(0)
+    d, n, nq, k = 128, 100_000, 1000, 10
+    xb = rs.rand(n, d).astype(np.float32)
+    xq = rs.rand(nq, d).astype(np.float32)
+    g, o = _mk_pair("flat", d, IP)
+    g.add(xb); o.add(xb)
+    Dg, Ig = g.search(xq, k)
+    sel = np.arange(0, nq, 25)
+    Do, Io = o.search(xq[sel], k)
+    _assert_same(Dg[sel], Ig[sel], Do, Io, "flat 100k")
+    # sortedness + self-consistency at full size
+    assert (np.diff(Dg, axis=1) <= 0).all()
+
+
+def test_flat_edge_cases():
+    rs = np.random.RandomState(2)
+    d = 32
+    g, o = _mk_pair("flat", d, IP)
+    xq = rs.rand(3, d).astype(np.float32)
+    D, I = g.search(xq, 4)  # empty index
+    assert (I == -1).all() and (D == -np.finfo(np.float32).max).all()
+    xb = rs.rand(3, d).astype(np.float32)
+    xb[2] = xb[0]  # exact duplicate -> tie broken by id
+    g.add(xb); o.add(xb)
+    _assert_same(*g.search(xq, 5), *o.search(xq, 5), "flat k > ntotal with ties")
+
+
+# ------------------------------------------------------------------ IVF kinds
+def _build_both(kind, metric, d, nlist, M, n, rs, via="gpu"):
+    """train+add on one side, ship the state to the other, so that both hold the SAME shard"""
+    xb = clustered(rs, n, d, ncl=max(8, nlist // 2))
+    g, o = _mk_pair(kind, d, metric, nlist=nlist, M=M)
+    if via == "gpu":
+        g.train(xb[: n // 2])
+        g.add(xb[: n // 3]); g.add(xb[n // 3:])
+        st = g.get_state()
+        o.set_state(st)
+        if kind == "ivf_pq":  # K7: per-vector term computed on device == oracle's
+            assert np.array_equal(st["tvals"], o.tvals)
+    else:
+        o.train(xb[: n // 2])
+        o.add(xb)
+        g.set_state(o.get_state())
+        if kind == "ivf_pq":
+            assert np.array_equal(g.get_array("tvals"), o.tvals)
+    assert g.ntotal == n == o.ntotal
+    return g, o, xb
+
+
+CASES = [
+    ("ivf_flat", L2, 64, 16, 0),
+    ("ivf_flat", IP, 64, 16, 0),
+    ("ivf_pq", L2, 64, 16, 16),
+    ("ivf_pq", L2, 128, 32, 32),
+    ("ivf_pq", IP, 128, 16, 32),   # knnlm with metric="dot": IP coarse quantizer, L2 PQ (quirk B2)
+    ("ivf_pq", L2, 96, 16, 24),    # generic-M code path
+    ("ivf_sq", L2, 64, 16, 0),
+    ("ivf_sq", L2, 768, 8, 0),
+]
+
+
+@pytest.mark.parametrize("kind,metric,d,nlist,M", CASES)
+@pytest.mark.parametrize("via", ["gpu", "oracle"])
+def test_ivf_matches_oracle(kind, metric, d, nlist, M, via):
+    rs = np.random.RandomState(3)
+    n = 6000
+    g, o, xb = _build_both(kind, metric, d, nlist, M, n, rs, via=via)
+    xq = np.concatenate([clustered(rs, 20, d, ncl=8), xb[:5] + 0.01 * rs.randn(5, d).astype(np.float32)])
+    for nprobe in (nlist, 1, 5):  # full nprobe first: the north-star parity condition
+        g.nprobe = nprobe; o.nprobe = nprobe
+        for k in (10, 1, 100):
+            Dg, Ig = g.search(xq, k)
+            Do, Io = o.search(xq, k)
+            _assert_same(Dg, Ig, Do, Io, f"{kind} metric={metric} d={d} via={via} nprobe={nprobe} k={k}")
+        assert g.last_stats()["ndis"] == o.last_ndis
+
+
+@pytest.mark.parametrize("kind,metric,d,nlist,M", [c for c in CASES if c[2] <= 128])
+def test_ivf_close_to_float64_restatement(kind, metric, d, nlist, M):
+    """GPU distances vs the independent float64 restatement: |dg - d64| <= 1e-4 * scale."""
+    from oracle import ref_numpy as R
+
+    rs = np.random.RandomState(4)
+    g, o, xb = _build_both(kind, metric, d, nlist, M, 4000, rs)
+    xq = clustered(rs, 16, d, ncl=8)
+    g.nprobe = nlist
+    Dg, Ig = g.search(xq, 10)
+    D64, I64 = R.ivf_search(g.get_state(), xq, nlist, 10)
+    scale = (xq.astype(np.float64) ** 2).sum(1, keepdims=True) + (xb.astype(np.float64) ** 2).sum(1).max()
+    assert (np.abs(Dg - D64) <= 1e-4 * scale).all()
+    assert (Ig == I64).mean() > 0.98  # ids differ only where float64 distances are within fp32 rounding
+
+
+def test_ivf_edge_cases():
+    """k > hits (-1 / FLT_MAX padding), empty lists, nprobe > nlist, single-vector lists, ties."""
+    from oracle import oracle as O
+
+    rs = np.random.RandomState(5)
+    d, nlist = 32, 8
+    E = _engine()
+    for kind, M in (("ivf_flat", 0), ("ivf_pq", 8), ("ivf_sq", 0)):
+        o = O.make_index(kind, d, metric=L2, nlist=nlist, M=M)
+        xb = clustered(rs, 600, d, ncl=4, sigma=0.05)  # 4 clusters, 8 lists -> some lists tiny/empty
+        xb[10:20] = xb[0]  # exact duplicates -> exact ties
+        o.train(xb); o.add(xb[:37])  # few vectors: most lists empty
+        kinds = {"ivf_flat": E.KIND_IVF_FLAT, "ivf_pq": E.KIND_IVF_PQ, "ivf_sq": E.KIND_IVF_SQ16}
+        g = E.GpuIndex(kinds[kind], d, L2, nlist=nlist, pq_m=M)
+        g.set_state(o.get_state())
+        xq = xb[:9]
+        for nprobe in (1, 3, 50):
+            g.nprobe = nprobe; o.nprobe = nprobe
+            Dg, Ig = g.search(xq, 64)
+            Do, Io = o.search(xq, 64)
+            _assert_same(Dg, Ig, Do, Io, f"edge {kind} nprobe={nprobe}")
+            assert (Ig == -1).any()
+            assert (Dg[Ig == -1] == np.finfo(np.float32).max).all()
+
+
+def test_ivfpq_larger_property():
+    """A shard too big for the oracle to scan exhaustively in seconds: compare on a query sample,
+    and check size-independent properties on the full batch (sortedness, ids valid and unique,
+    batch invariance, idempotence)."""
+    rs = np.random.RandomState(6)
+    d, nlist, M, n = 128, 256, 32, 300_000
+    g, o, xb = _build_both("ivf_pq", L2, d, nlist, M, n, rs)
+    xq = xb[rs.randint(0, n, 512)] + 0.02 * rs.randn(512, d).astype(np.float32)
+    g.nprobe = 16; o.nprobe = 16
+    Dg, Ig = g.search(xq, 10)
+    assert (np.diff(Dg, axis=1) >= 0).all()
+    assert ((Ig >= 0) & (Ig < n)).all()
+    assert all(len(set(r)) == len(r) for r in Ig.tolist())
+    D2, I2 = g.search(xq, 10)
+    assert np.array_equal(Dg, D2) and np.array_equal(Ig, I2)
+    D1, I1 = g.search(xq[100:101], 10)  # batch invariance: same answer alone or in a batch
+    assert np.array_equal(D1[0], Dg[100]) and np.array_equal(I1[0], Ig[100])
+    sel = np.arange(0, 512, 16)
+    Do, Io = o.search(xq[sel], 10)
+    _assert_same(Dg[sel], Ig[sel], Do, Io, "ivf_pq 300k sample")
+
+
+# ------------------------------------------------------------------ K6 merge
+def test_merge_reference_golden():
+    """golden vectors of reference tests/test_integration.py:181-203"""
+    import json, os
+
+    E = _engine()
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "merge_golden.json")))
+    D = np.array(gold["shard_D"], dtype=np.float32)  # [S, nq, k]
+    meta = gold["shard_meta"]
+    S, nq, k = D.shape
+    pos = np.arange(S * nq * k, dtype=np.int64).reshape(S, nq, k)
+    flat_meta = [m for s in meta for row in s for m in row]
+    for negate, key in ((False, "minimize"), (True, "maximize")):
+        outD, outP = E.merge(D, pos, negate=negate)
+        assert [flat_meta[p] for p in outP[0]] == gold[key]["meta"][0]
+        assert np.allclose(outD[0], np.array(gold[key]["D"][0], dtype=np.float32), rtol=0, atol=0)
+
+
+@pytest.mark.parametrize("S,nq,k", [(2, 1, 4), (8, 64, 10), (4, 300, 100), (8, 4096, 10), (3, 5, 1)])
+def test_merge_matches_oracle(S, nq, k):
+    from oracle import oracle as O
+
+    E = _engine()
+    rs = np.random.RandomState(7)
+    D = np.sort(rs.rand(S, nq, k).astype(np.float32), axis=2)
+    D[rs.rand(S, nq, k) < 0.05] = np.finfo(np.float32).max  # shards with missing hits
+    D[0, :, : k // 2] = D[1 % S, :, : k // 2]  # cross-shard ties: earlier shard must win
+    I = rs.randint(0, 1 << 40, size=(S, nq, k)).astype(np.int64)
+    I[D == np.finfo(np.float32).max] = -1
+    for negate in (False, True):
+        Dx = -D if negate else D
+        outD, outI = E.merge(Dx, I, negate=negate)
+        pos = np.arange(S * nq * k, dtype=np.int64).reshape(S, nq, k)
+        refD, refP = O.merge(-Dx if negate else Dx, pos)
+        refI = np.where(refP >= 0, I.reshape(-1)[np.maximum(refP, 0)], -1)
+        assert np.array_equal(outD, refD)
+        assert np.array_equal(outI, refI)
+
+
+# ------------------------------------------------------------------ reconstruct / accessors
+def test_reconstruct_and_centroids():
+    rs = np.random.RandomState(8)
+    for kind, M in (("ivf_flat", 0), ("ivf_pq", 16), ("ivf_sq", 0)):
+        g, o, xb = _build_both(kind, L2, 64, 16, M, 3000, rs)
+        ids = np.array([0, 5, 2999, -1, 17], dtype=np.int64)
+        R_g = g.reconstruct_rows(ids)
+        R_o = o.reconstruct_rows(ids)
+        assert np.isnan(R_g[3]).all()
+        ok = [0, 1, 2, 4]
+        assert np.allclose(R_g[ok], R_o[ok], rtol=0, atol=1e-6)
+        assert np.array_equal(g.quantizer.reconstruct_n(0, 16), o.quantizer.reconstruct_n(0, 16))
+        D, I, R = g.search_and_reconstruct(xb[:4], 3)
+        assert R.shape == (4, 3, 64)
+
+
+def test_gpu_training_quality():
+    """GPU k-means / PQ training is not bit-comparable to the oracle's (different sampling), but
+    its quantisation error must be in the same range as the oracle's on the same data."""
+    from oracle import oracle as O
+
+    rs = np.random.RandomState(9)
+    d, nlist, M, n = 64, 32, 16, 20000
+    xb = clustered(rs, n, d, ncl=40, sigma=0.2)
+    g, o = _mk_pair("ivf_pq", d, L2, nlist=nlist, M=M)
+    g.train(xb); g.add(xb)
+    o.train(xb); o.add(xb)
+
+    def recon_err(ix):
+        R = ix.reconstruct_rows(np.arange(0, n, 7, dtype=np.int64))
+        return float(((R - xb[::7]) ** 2).sum(1).mean())
+
+    eg, eo = recon_err(g), recon_err(o)
+    assert eg < 1.25 * eo + 1e-6, (eg, eo)
+    lens = np.diff(g.get_array("list_off"))
+    assert lens.sum() == n and (lens > 0).sum() >= nlist // 2
