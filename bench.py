@@ -1,0 +1,462 @@
+#!/usr/bin/env python
+"""bench.py -- QPS at recall@10 >= 0.95, IVF-PQ d=128, 1B synthetic vectors, 8 shards.
+
+Contract (see the task statement): `python bench.py --gpus N --steps K --warmup W` prints ONE
+JSON line from rank 0.  A "step" is one pass of the hot path (IndexClient.search fan-out ->
+coarse quantizer -> PQ table -> inverted-list scan -> cross-shard merge) over one batch of
+`--batch` synthetic queries.  N>1 is launched by torchrun (one rank per GPU, NCCL).
+
+Workload (BASELINE.json configs[4]): N vectors, d=128, 8 shards (row block b of
+50 000 rows -> shard b mod 8, mimicking the client's round-robin), every shard its own IVF-PQ
+(M=32 x 8 bit, nlist per shard by size tier), k=10, nprobe = smallest power of two whose
+recall@10 (|top10 ∩ exact top10| / 10) on held-out queries is >= 0.95.  With N GPUs each rank
+holds 8/N shards (total work fixed -> "strong" scaling).
+
+`--impl reference` times the CPU restatement of the reference's FAISS path (oracle/, all host
+threads) on a bounded sample of the same workload; see cpu_baseline.sample in the output.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BLOCK = 50_000   # rows per round-robin block (reference buffer_bsz default, index_cfg.py:23)
+NSHARDS = 8
+D = 128
+K = 10
+PQ_M = 32
+
+
+def log(*a):
+    if int(os.environ.get("RANK", "0")) == 0:
+        print("[bench]", *a, file=sys.stderr, flush=True)
+
+
+def nlist_for(n_shard: int) -> int:
+    if n_shard >= 50_000_000:
+        return 65536
+    if n_shard >= 5_000_000:
+        return 16384
+    if n_shard >= 500_000:
+        return 4096
+    return 1024
+
+
+# ---------------------------------------------------------------------------------------------
+def shard_rows(nvec: int, shard: int):
+    """(first_row, n_rows) of every block owned by `shard`, in arrival order."""
+    nblocks = (nvec + BLOCK - 1) // BLOCK
+    out = []
+    for b in range(shard, nblocks, NSHARDS):
+        r0 = b * BLOCK
+        out.append((r0, min(BLOCK, nvec - r0)))
+    return out
+
+
+def build_shard(engine, synth, nvec, shard, args, torch):
+    """generate -> train -> add, all on device.  Returns (GpuIndex, id_table int64 [n_shard])."""
+    blocks = shard_rows(nvec, shard)
+    n_shard = sum(n for _, n in blocks)
+    nlist = args.nlist or nlist_for(n_shard)
+    idx = engine.GpuIndex(engine.KIND_IVF_PQ, D, engine.METRIC_L2, nlist=nlist, pq_m=PQ_M)
+    idx.set_param("kmeans_niter", args.kmeans_niter)
+    idx.set_param("max_points_per_centroid", args.train_pts)
+    idx.reserve(n_shard)
+    # training set = the first rows of the shard (reference trains on the first train_num rows)
+    n_train = min(n_shard, args.train_pts * nlist)
+    xs, got = [], 0
+    for r0, n in blocks:
+        take = min(n, n_train - got)
+        xs.append(synth.rows(r0, take))
+        got += take
+        if got >= n_train:
+            break
+    xt = torch.cat(xs) if len(xs) > 1 else xs[0]
+    t0 = time.time()
+    idx.train_dev(xt)
+    torch.cuda.synchronize()
+    t_train = time.time() - t0
+    del xt, xs
+    t0 = time.time()
+    ids = []
+    group = max(1, (1 << 20) // BLOCK)  # add ~1M rows per call
+    buf = torch.empty((group * BLOCK, D), dtype=torch.float32, device="cuda")
+    for g0 in range(0, len(blocks), group):
+        part = blocks[g0:g0 + group]
+        off = 0
+        for r0, n in part:
+            synth.rows(r0, n, out_t=buf[off:off + n])
+            ids.append(torch.arange(r0, r0 + n, dtype=torch.int64, device="cuda"))
+            off += n
+        idx.add_dev(buf[:off])
+    idx.finalize()
+    torch.cuda.synchronize()
+    t_add = time.time() - t0
+    del buf
+    return idx, torch.cat(ids), {"nlist": nlist, "n": n_shard, "train_s": t_train, "add_s": t_add}
+
+
+def ground_truth(synth, nvec, q_rows, xq, args, torch):
+    """Exact top-K of every query, using the generator's structure: row i belongs to cluster
+    i mod C, points of a cluster lie within R = sigma*4*sqrt(r) of its centre (latents are clipped
+    to |z|<=4), so the exact neighbours are the best rows of the query's own cluster whenever the
+    K-th of them is closer than (distance to the nearest OTHER centre - R); that condition is
+    checked for every query and violations are counted (and reported)."""
+    C = synth.p.nclusters
+    R = synth.p.sigma * 4.0 * (synth.p.r ** 0.5)
+    nq = xq.shape[0]
+    gt = torch.full((nq, K), -1, dtype=torch.int64, device="cuda")
+    dk = torch.empty((nq,), dtype=torch.float32, device="cuda")
+    per = (nvec + C - 1) // C
+    chunk = max(1, (256 << 20) // (per * D * 4))
+    for q0 in range(0, nq, chunk):
+        qr = q_rows[q0:q0 + chunk]
+        c = qr % C
+        j = torch.arange(per, device="cuda", dtype=torch.int64)
+        rows = c[:, None] + j[None, :] * C                       # [cq, per]
+        valid = rows < nvec
+        rows_c = torch.where(valid, rows, c[:, None].expand_as(rows))
+        x = synth.rows(0, rows_c.numel(), rows_t=rows_c.reshape(-1).contiguous()).view(rows.shape[0], per, D)
+        dist = ((x - xq[q0:q0 + chunk, None, :]) ** 2).sum(-1)
+        dist = torch.where(valid, dist, torch.full_like(dist, float("inf")))
+        # order by (distance, row) like the engine does
+        dv, di = torch.sort(dist, dim=1, stable=True)
+        gt[q0:q0 + chunk] = torch.gather(rows, 1, di[:, :K])
+        dk[q0:q0 + chunk] = dv[:, K - 1]
+    # certification: distance to the nearest other centre
+    cent = synth_centres(synth, torch)
+    viol = 0
+    for q0 in range(0, nq, 1024):
+        dc = torch.cdist(xq[q0:q0 + 1024], cent)                  # [cq, C]
+        own = (q_rows[q0:q0 + 1024] % C)
+        dc.scatter_(1, own[:, None], float("inf"))
+        lb = dc.min(dim=1).values - R
+        viol += int((dk[q0:q0 + 1024].sqrt() > lb).sum().item())
+    return gt, viol
+
+
+_centres_cache = {}
+
+
+def synth_centres(synth, torch):
+    """the C cluster centres (the generator at sigma = 0; row c belongs to cluster c)"""
+    key = id(synth)
+    if key not in _centres_cache:
+        from distributed_faiss_b200 import engine
+
+        p = synth.p
+        s0 = engine.Synth(p.seed, p.d, p.r, p.nclusters, 0.0)
+        _centres_cache[key] = s0.rows(0, p.nclusters)
+    return _centres_cache[key]
+
+
+def recall_at_k(I, gt):
+    hits = (I[:, :, None] == gt[:, None, :]).any(-1).sum(-1).float()
+    return float(hits.mean().item() / K)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, gpu_index):
+        self.rows = []
+        self.proc = None
+        self.gpu = gpu_index
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.gpu), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i] == "Active" for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------
+def cpu_baseline(shard_idx_obj, xq_np, nprobe, nq_cpu, n_shards_total):
+    """The reference's CPU path (oracle restatement), all host threads, on ONE shard of the
+    workload; system QPS = shard QPS / n_shards (the same host serves every shard)."""
+    from oracle import oracle as O
+
+    st = shard_idx_obj.get_state()
+    o = O.OracleIVFPQ(D, st["nlist"], PQ_M, 8, coarse_metric=O.METRIC_L2)
+    o.set_state(st, recompute_tvals=False)
+    o.nprobe = nprobe
+    q = xq_np[:nq_cpu]
+    o.search(q[:32], K)  # warm-up
+    t0 = time.perf_counter()
+    Do, Io = o.search(q, K)
+    dt = time.perf_counter() - t0
+    return {"value": (len(q) / dt) / n_shards_total, "unit": "QPS", "cores": O.num_threads(), "kind": "port",
+            "sample": f"shard 0 of {n_shards_total} ({o.ntotal} vectors, nlist {o.nlist}), {len(q)} queries, "
+                      f"nprobe {nprobe}, {dt:.2f} s; system QPS = shard QPS / {n_shards_total}",
+            "_D": Do, "_I": Io}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--nvec", type=int, default=int(os.environ.get("DFX_BENCH_NVEC", 1_000_000_000)))
+    ap.add_argument("--batch", type=int, default=4096)
+    ap.add_argument("--nprobe", type=int, default=0, help="0 = smallest power of two reaching the recall gate")
+    ap.add_argument("--nlist", type=int, default=0)
+    ap.add_argument("--nq-pool", type=int, default=10000)
+    ap.add_argument("--kmeans-niter", type=int, default=10)
+    ap.add_argument("--train-pts", type=int, default=64, help="training points per centroid")
+    ap.add_argument("--clusters", type=int, default=0, help="generator clusters (0 = nvec/1024)")
+    ap.add_argument("--rank-dim", type=int, default=16)
+    ap.add_argument("--sigma", type=float, default=0.15)
+    ap.add_argument("--sigma-q", type=float, default=0.02)
+    ap.add_argument("--cpu-queries", type=int, default=512)
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--sweep", action="store_true", help="also time batch sizes 1, 64, 512")
+    args = ap.parse_args()
+
+    import torch
+
+    from distributed_faiss_b200 import engine, spmd
+
+    rank, local_rank, world = spmd.init_process_group_from_env()
+    if args.impl == "reference" and rank != 0:
+        return 0
+    assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback)"
+    assert NSHARDS % world == 0, "--gpus must divide 8"
+    dist = torch.distributed
+    nvec = args.nvec
+    C = args.clusters or max(1, nvec // 1024)
+    synth = engine.Synth(1234, D, args.rank_dim, C, args.sigma, args.sigma_q)
+
+    # ---------------- build this rank's shards
+    s_loc = NSHARDS // world
+    my_shards = list(range(rank * s_loc, (rank + 1) * s_loc))
+    if args.impl == "reference":
+        my_shards = [0]
+    t_build0 = time.time()
+    shards, tables, infos = [], [], []
+    for s in my_shards:
+        idx, tab, info = build_shard(engine, synth, nvec, s, args, torch)
+        shards.append(idx)
+        tables.append(tab)
+        infos.append(info)
+        log(f"shard {s}: {info}")
+    build_s = time.time() - t_build0
+    group = spmd.ShardGroup(shards, tables)
+
+    # ---------------- queries + exact ground truth
+    g = torch.Generator(device="cpu").manual_seed(1236)
+    q_rows = torch.randint(0, nvec, (args.nq_pool,), generator=g, dtype=torch.int64).cuda()
+    xq = synth.rows(0, args.nq_pool, rows_t=q_rows, noise_stream=7)
+    n_eval = min(2000, args.nq_pool)
+    gt, gt_viol = ground_truth(synth, nvec, q_rows[:n_eval], xq[:n_eval], args, torch)
+
+    def run_search(x, nprobe):
+        group.set_nprobe(nprobe)
+        return group.search(x, K, maximize=False)
+
+    # ---------------- reference arm: CPU only
+    if args.impl == "reference":
+        nprobe = args.nprobe or 32
+        xq_np = xq.cpu().numpy()
+        vals = []
+        for it in range(args.warmup + args.steps):
+            cb = cpu_baseline(shards[0], xq_np[(it * args.cpu_queries) % (args.nq_pool - args.cpu_queries):], nprobe,
+                              args.cpu_queries, NSHARDS)
+            if it >= args.warmup:
+                vals.append(cb["value"])
+        cb.pop("_D"), cb.pop("_I")
+        v = float(np.mean(vals))
+        cb["value"] = v
+        out = {"impl": "reference", "metric": "QPS at recall@10>=0.95, IVF-PQ d=128", "value": v, "unit": "QPS",
+               "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+               "ms_per_step": 1e3 * args.cpu_queries / (v * NSHARDS) if v else None,
+               "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+               "config": {"workload": workload_name(nvec), "nprobe": nprobe, "batch": args.cpu_queries},
+               "cpu_baseline": cb,
+               "e2e": {"value": v, "unit": "QPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(out), flush=True)
+        return 0
+
+    # ---------------- nprobe: smallest power of two meeting the recall gate
+    recalls = {}
+    nprobe = args.nprobe
+    if not nprobe:
+        for cand in (1, 2, 4, 8, 16, 32, 64, 128, 256, 512):
+            if cand > shards[0].nlist:
+                break
+            _, I = run_search(xq[:n_eval].contiguous(), cand)
+            recalls[cand] = recall_at_k(I, gt)
+            log(f"nprobe {cand}: recall@10 = {recalls[cand]:.4f}")
+            nprobe = cand
+            if recalls[cand] >= 0.95:
+                break
+    _, I = run_search(xq[:n_eval].contiguous(), nprobe)
+    recall = recall_at_k(I, gt)
+    r1 = float((I[:, :1] == gt[:, :1]).float().mean().item())
+
+    # ---------------- timed region (device-resident inputs)
+    B = args.batch
+    nb = max(1, args.nq_pool // B)
+    batches = [xq[i * B:(i + 1) * B].contiguous() for i in range(nb)] if B <= args.nq_pool else [xq.repeat((B // args.nq_pool) + 1, 1)[:B].contiguous()]
+
+    def timed(batches_, steps, warmup, host=False):
+        host_batches = [b.cpu().numpy() for b in batches_] if host else None
+        for it in range(warmup):
+            if host:
+                group.search_host(host_batches[it % len(batches_)], K)
+            else:
+                group.search(batches_[it % len(batches_)], K)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for it in range(steps):
+            if host:
+                group.search_host(host_batches[it % len(batches_)], K)
+            else:
+                group.search(batches_[it % len(batches_)], K)
+        e1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    group.set_nprobe(nprobe)
+    # ndis per batch (untimed) for the roofline's algorithmic bytes
+    ndis_per_batch = []
+    for b in batches:
+        group.search(b, K)
+        ndis_per_batch.append(sum(s.last_stats()["ndis"] for s in shards))
+    for s in shards:
+        s.profile(True)
+        s.profile_read(reset=True)
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    launches0 = engine.launch_count()
+    ms = timed(batches, args.steps, args.warmup)
+    launches = engine.launch_count() - launches0
+    clk = clocks.stop()
+    scan_ms, scan_launches = 0.0, 0
+    for s in shards:
+        m, n = s.profile_read(reset=True)
+        scan_ms += m
+        scan_launches += n
+        s.profile(False)
+    # the profile covers warm-up + timed launches alike; per-launch averages are what is used
+    qps = args.steps * B / (ms / 1e3)
+    ndis_step = float(np.mean([ndis_per_batch[it % len(batches)] for it in range(args.steps)]))
+    launches_timed = launches * args.steps // (args.steps + args.warmup)
+
+    # e2e: host buffers through the public call, H2D + D2H inside the timed region
+    ms_e2e = timed(batches, args.steps, args.warmup, host=True)
+    qps_e2e = args.steps * B / (ms_e2e / 1e3)
+
+    sweep = {}
+    if args.sweep:
+        for b in (1, 64, 512):
+            bb = [xq[i * b:(i + 1) * b].contiguous() for i in range(min(32, args.nq_pool // b))]
+            st = max(args.steps, 50 if b <= 64 else args.steps)
+            t = timed(bb, st, args.warmup)
+            sweep[str(b)] = st * b / (t / 1e3)
+
+    # roofline of the dominant kernel (scan_pq): algorithmic bytes = ndis * code_bytes
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+    per_launch_ms = scan_ms / max(scan_launches, 1)
+    # this rank's launches cover its local shards; bytes per launch = ndis of one shard-search
+    bytes_per_launch = (ndis_step / max(len(shards), 1)) * PQ_M
+    # (chunked searches split a batch into several launches; account for that)
+    launches_per_search = max(1, round(scan_launches / max((args.steps + args.warmup) * len(shards), 1)))
+    bytes_per_launch /= launches_per_search
+    achieved = bytes_per_launch / (per_launch_ms * 1e-3) / 1e9 if per_launch_ms > 0 else 0.0
+    scan_ms_per_step = scan_ms / (args.steps + args.warmup)
+    roofline = {"kernel": "scan_pq_kernel<32>", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "bytes_per_launch": bytes_per_launch, "ms_per_launch": per_launch_ms,
+                "launches_per_step": scan_launches / (args.steps + args.warmup),
+                "scan_share_of_step": scan_ms_per_step / (ms / args.steps) if ms else None}
+
+    cb = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cb = cpu_baseline(shards[0], xq.cpu().numpy(), nprobe, args.cpu_queries, NSHARDS)
+        # cross-check on the way: the GPU shard and the oracle agree bit for bit on this sample
+        shards[0].nprobe = nprobe
+        Dg, Ig = shards[0].search(xq[:args.cpu_queries].cpu().numpy(), K)
+        cb["gpu_equals_oracle"] = bool(np.array_equal(Dg, cb.pop("_D")) and np.array_equal(Ig, cb.pop("_I")))
+
+    if rank == 0:
+        out = {
+            "metric": "QPS at recall@10>=0.95, IVF-PQ d=128", "value": qps, "unit": "QPS", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32 (u8 PQ codes, f32 tables/accumulate)",
+            "data": "synthetic",
+            "config": {"workload": workload_name(nvec), "nvec": nvec, "shards": NSHARDS, "shards_per_gpu": s_loc,
+                       "nlist_per_shard": infos[0]["nlist"], "pq": "M=32 x 8 bit", "k": K, "nprobe": nprobe,
+                       "batch": B, "recall_at_10": recall, "recall_1_at_1": r1, "recall_by_nprobe": recalls,
+                       "gt_uncertified_queries": gt_viol, "l2_flush": "working set (PQ codes) >> 126 MB L2",
+                       "generator": {"clusters": C, "rank": args.rank_dim, "sigma": args.sigma, "sigma_q": args.sigma_q},
+                       "train": {"kmeans_niter": args.kmeans_niter, "points_per_centroid": args.train_pts},
+                       "build_seconds": build_s, "ndis_per_step": ndis_step},
+            "e2e": {"value": qps_e2e, "unit": "QPS", "h2d_bytes_per_step": B * D * 4, "d2h_bytes_per_step": B * K * 12,
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches_timed),
+            "clocks": clk,
+            "roofline": roofline,
+            "cpu_baseline": cb,
+        }
+        if sweep:
+            out["config"]["qps_by_batch"] = sweep
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def workload_name(nvec):
+    return f"IVF-PQ d=128, {nvec / 1e9:g}B synthetic vectors, 8 shards, k=10 (BASELINE configs[4])"
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -90,6 +90,10 @@ void dfx_destroy(dfx_index* idx) {
             cudaStreamSynchronize(idx->stream);
             cudaStreamDestroy(idx->stream);
         }
+        for (auto& e : idx->prof_events) {
+            cudaEventDestroy(e.first);
+            cudaEventDestroy(e.second);
+        }
         delete idx;
     }
 }
@@ -263,6 +267,29 @@ int dfx_last_stats(dfx_index* idx, int64_t* ndis, int64_t* nq, int64_t* nprobe) 
     if (ndis) *ndis = nd;
     if (nq) *nq = idx->last_nq;
     if (nprobe) *nprobe = idx->last_nprobe;
+    DFX_API_END
+}
+
+int dfx_profile_enable(dfx_index* idx, int on) {
+    DFX_API_BEGIN
+    std::lock_guard<std::mutex> lk(idx->mu);
+    idx->prof_on = on != 0;
+    DFX_API_END
+}
+int dfx_profile_read(dfx_index* idx, double* scan_ms, int64_t* scan_launches, int reset) {
+    DFX_API_BEGIN
+    std::lock_guard<std::mutex> lk(idx->mu);
+    DeviceGuard g(idx->cfg.device);
+    double ms = 0;
+    for (size_t i = 0; i < idx->prof_used; i++) {
+        DFX_CUDA(cudaEventSynchronize(idx->prof_events[i].second));
+        float t = 0;
+        DFX_CUDA(cudaEventElapsedTime(&t, idx->prof_events[i].first, idx->prof_events[i].second));
+        ms += t;
+    }
+    if (scan_ms) *scan_ms = ms;
+    if (scan_launches) *scan_launches = (int64_t)idx->prof_used;
+    if (reset) idx->prof_used = 0;
     DFX_API_END
 }
 

@@ -190,17 +190,9 @@ void dfx_assign_impl(dfx_index* idx, const float* d_cent, const float* d_cnorm, 
                      int metric, int d, int64_t n, const float* d_x, int32_t* d_assign,
                      cudaStream_t st) {
     if (n <= 0) return;
-    int64_t RC = (32ll << 20) / nlist;
-    if (RC < 1) RC = 1;
-    if (RC > n) RC = n;
-    idx->w_vals.reserve((size_t)RC * nlist * 4);
-    for (int64_t r0 = 0; r0 < n; r0 += RC) {
-        int64_t rc = std::min(RC, n - r0);
-        dfx_launch_gemm_values(d_x + r0 * d, rc, d_cent, d_cnorm, nlist, d, metric,
-                               idx->w_vals.as<float>(), nlist, st);
-        dfx_launch_select_cols(idx->w_vals.as<float>(), rc, (int)nlist, nlist, 1, 0, d_assign + r0,
-                               nullptr, nullptr, 0, st);
-    }
+    idx->w_best.reserve((size_t)n * 8);
+    dfx_launch_assign_fused(d_x, n, d_cent, d_cnorm, nlist, d, metric,
+                            idx->w_best.as<unsigned long long>(), d_assign, st);
 }
 
 // ------------------------------------------------------------------ k-means on device

@@ -26,7 +26,7 @@ struct dfx_index {
     int64_t reserve_hint = 0;
 
     // search workspace (grow-only)
-    DevBuf w_vals, w_keys, w_dis0, w_lut, w_part, w_q, w_D, w_I, w_misc;
+    DevBuf w_vals, w_keys, w_dis0, w_lut, w_part, w_q, w_D, w_I, w_misc, w_best;
     // reconstruct support: inverse of ids (shard-local id -> storage position)
     DevBuf inv;
     bool inv_valid = false;
@@ -34,6 +34,11 @@ struct dfx_index {
     int kmeans_niter = 25;            // faiss Clustering default niter
     int max_points_per_centroid = 256;  // faiss Clustering default
     uint64_t train_seed = 1234;       // faiss Clustering default seed
+
+    // scan-kernel profiling (dfx_profile_enable)
+    bool prof_on = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
+    size_t prof_used = 0;
 
     // last-search bookkeeping
     int64_t last_nq = 0, last_nprobe = 0;
@@ -79,6 +84,10 @@ void dfx_add_impl(dfx_index* idx, int64_t n, const float* d_x, cudaStream_t st);
 void dfx_finalize_impl(dfx_index* idx, cudaStream_t st);
 void dfx_reconstruct_impl(dfx_index* idx, int64_t n, const int64_t* d_ids, float* d_out,
                           cudaStream_t st);
+// fused nearest-centroid (GEMM + argmin epilogue), no values matrix
+void dfx_launch_assign_fused(const float* X, int64_t n, const float* cent, const float* cnorm,
+                             int64_t nlist, int d, int metric, unsigned long long* best,
+                             int32_t* out, cudaStream_t st);
 void dfx_assign_impl(dfx_index* idx, const float* d_cent, const float* d_cnorm, int64_t nlist,
                      int metric, int d, int64_t n, const float* d_x, int32_t* d_assign,
                      cudaStream_t st);

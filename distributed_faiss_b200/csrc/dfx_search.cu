@@ -648,6 +648,17 @@ void dfx_search_impl(dfx_index* idx, int64_t nq, const float* d_x, int64_t k64, 
         const int ngroups = (nprobe + G - 1) / G;
         idx->w_part.reserve((size_t)qc * ngroups * k * 8);
         uint64_t* part = idx->w_part.as<uint64_t>();
+        std::pair<cudaEvent_t, cudaEvent_t>* pev = nullptr;
+        if (idx->prof_on) {
+            if (idx->prof_used == idx->prof_events.size()) {
+                cudaEvent_t a, b;
+                DFX_CUDA(cudaEventCreate(&a));
+                DFX_CUDA(cudaEventCreate(&b));
+                idx->prof_events.emplace_back(a, b);
+            }
+            pev = &idx->prof_events[idx->prof_used++];
+            DFX_CUDA(cudaEventRecord(pev->first, st));
+        }
 
         if (kind == DFX_IVF_PQ) {
             const int M = idx->M, ksub = idx->ksub;
@@ -689,6 +700,7 @@ void dfx_search_impl(dfx_index* idx, int64_t nq, const float* d_x, int64_t k64, 
             else DFX_SCAN_ROWS(1);
 #undef DFX_SCAN_ROWS
         }
+        if (pev) DFX_CUDA(cudaEventRecord(pev->second, st));
         CompLoader ldr{part, (int64_t)ngroups * k};
         ResultWriter wr{d_D + q0 * k, d_I + q0 * k, k, smetric, 0.f, nullptr};
         dfx_launch_select<128>(ldr, wr, qc, ngroups * k, k, st);
@@ -696,4 +708,103 @@ void dfx_search_impl(dfx_index* idx, int64_t nq, const float* d_x, int64_t k64, 
     idx->last_nq = nq;
     idx->last_nprobe = nprobe;
     idx->last_keys_valid = true;
+}
+
+// =====================================================================================
+// K7a: fused nearest-centroid assignment (build path).  Same FFMA tile as K1a, but the
+// epilogue reduces each row's tile to one composite (value, column) and folds it into
+// best[row] with a 64-bit atomicMin -- the values matrix is never written.  The minimum of
+// composites is exactly the oracle's argmin with ties -> smaller index.
+// =====================================================================================
+template <int BM, int BN, int BK, int TM, int TN>
+__global__ void __launch_bounds__((BM / TM) * (BN / TN))
+gemm_argmin_kernel(const float* __restrict__ Q, int64_t nq, const float* __restrict__ X,
+                   const float* __restrict__ xnorm, int64_t ncols, int d, int metric,
+                   unsigned long long* __restrict__ best) {
+    constexpr int THREADS = (BM / TM) * (BN / TN);
+    __shared__ float sQ[BK][BM + 4];
+    __shared__ float sX[BK][BN + 4];
+    const int tid = threadIdx.x;
+    const int tx = tid % (BN / TN), ty = tid / (BN / TN);
+    const int64_t m0 = (int64_t)blockIdx.y * BM;
+    const int64_t n0 = (int64_t)blockIdx.x * BN;
+    float acc[TM][TN];
+#pragma unroll
+    for (int i = 0; i < TM; i++)
+#pragma unroll
+        for (int j = 0; j < TN; j++) acc[i][j] = 0.f;
+    for (int k0 = 0; k0 < d; k0 += BK) {
+        for (int e = tid; e < BM * BK; e += THREADS) {
+            int m = e / BK, kk = e % BK;
+            int64_t gm = m0 + m;
+            int gk = k0 + kk;
+            sQ[kk][m] = (gm < nq && gk < d) ? Q[gm * d + gk] : 0.f;
+        }
+        for (int e = tid; e < BN * BK; e += THREADS) {
+            int n = e / BK, kk = e % BK;
+            int64_t gn = n0 + n;
+            int gk = k0 + kk;
+            sX[kk][n] = (gn < ncols && gk < d) ? X[gn * d + gk] : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < BK; kk++) {
+            float a[TM], b[TN];
+#pragma unroll
+            for (int i = 0; i < TM; i++) a[i] = sQ[kk][ty * TM + i];
+#pragma unroll
+            for (int j = 0; j < TN; j++) b[j] = sX[kk][tx * TN + j];
+#pragma unroll
+            for (int i = 0; i < TM; i++)
+#pragma unroll
+                for (int j = 0; j < TN; j++) acc[i][j] = __fmaf_rn(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+    constexpr int TXN = BN / TN;  // threads sharing a row (consecutive lanes)
+#pragma unroll
+    for (int i = 0; i < TM; i++) {
+        unsigned long long c = DFX_COMP_NONE;
+#pragma unroll
+        for (int j = 0; j < TN; j++) {
+            int64_t gn = n0 + tx * TN + j;
+            if (gn < ncols) {
+                float ip = acc[i][j];
+                float v = (metric == DFX_METRIC_IP) ? -ip : __fmaf_rn(-2.f, ip, xnorm[gn]);
+                unsigned long long cc = dfx_comp(v, (uint32_t)gn);
+                c = cc < c ? cc : c;
+            }
+        }
+#pragma unroll
+        for (int off = TXN / 2; off >= 1; off >>= 1) {
+            unsigned long long o = __shfl_xor_sync(0xffffffffu, c, off);
+            c = o < c ? o : c;
+        }
+        int64_t gm = m0 + ty * TM + i;
+        if (tx == 0 && gm < nq && c != DFX_COMP_NONE) atomicMin(&best[gm], c);
+    }
+}
+
+__global__ void unpack_best_kernel(const unsigned long long* __restrict__ best, int64_t n,
+                                   int32_t* __restrict__ out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (int32_t)(uint32_t)best[i];
+}
+
+void dfx_launch_assign_fused(const float* X, int64_t n, const float* cent, const float* cnorm,
+                             int64_t nlist, int d, int metric, unsigned long long* best,
+                             int32_t* out, cudaStream_t st) {
+    if (n <= 0) return;
+    DFX_CUDA(cudaMemsetAsync(best, 0xff, (size_t)n * 8, st));
+    constexpr int BM = 128, BN = 128, BK = 8, TM = 8, TN = 8;
+    static_assert(BN / TN == 16, "row group must be 16 consecutive lanes");
+    const int64_t max_y = 65535;
+    for (int64_t r0 = 0; r0 < n; r0 += max_y * BM) {
+        int64_t rc = std::min<int64_t>(n - r0, max_y * BM);
+        dim3 grid((unsigned)dfx_ceil_div(nlist, BN), (unsigned)dfx_ceil_div(rc, BM));
+        auto kern = gemm_argmin_kernel<BM, BN, BK, TM, TN>;
+        DFX_LAUNCH(kern, grid, (BM / TM) * (BN / TN), 0, st, X + r0 * d, rc, cent, cnorm, nlist, d, metric,
+                   best + r0);
+    }
+    DFX_LAUNCH(unpack_best_kernel, (unsigned)dfx_ceil_div(n, 256), 256, 0, st, best, n, out);
 }

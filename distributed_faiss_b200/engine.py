@@ -33,7 +33,7 @@ EXPORTED_SYMBOLS = [
     "dfx_reserve", "dfx_finalize", "dfx_search", "dfx_search_dev", "dfx_reconstruct", "dfx_set_nprobe",
     "dfx_get_nprobe", "dfx_ntotal", "dfx_nlist", "dfx_is_trained", "dfx_get_centroids", "dfx_merge",
     "dfx_merge_dev", "dfx_map_ids_dev", "dfx_get_array", "dfx_set_array", "dfx_import_done",
-    "dfx_last_stats", "dfx_launch_count", "dfx_synth_init", "dfx_synth_rows_dev", "dfx_free",
+    "dfx_last_stats", "dfx_profile_enable", "dfx_profile_read", "dfx_launch_count", "dfx_synth_init", "dfx_synth_rows_dev", "dfx_free",
     "dfx_last_error", "dfx_version",
 ]
 
@@ -226,6 +226,14 @@ class GpuIndex:
         ndis, nq, npb = C.c_int64(0), C.c_int64(0), C.c_int64(0)
         _check(lib().dfx_last_stats(self._h, C.byref(ndis), C.byref(nq), C.byref(npb)))
         return {"ndis": ndis.value, "nq": nq.value, "nprobe": npb.value}
+
+    def profile(self, on=True):
+        _check(lib().dfx_profile_enable(self._h, C.c_int(1 if on else 0)))
+
+    def profile_read(self, reset=True):
+        ms, n = C.c_double(0), C.c_int64(0)
+        _check(lib().dfx_profile_read(self._h, C.byref(ms), C.byref(n), C.c_int(1 if reset else 0)))
+        return ms.value, n.value
 
     # ---- state exchange (tests / persistence)
     _DTYPES = {"centroids": np.float32, "codebooks": np.float32, "list_off": np.int64, "ids": np.int64,

@@ -1,0 +1,154 @@
+"""NCCL data plane: the search fan-out of IndexClient.search over GPUs instead of sockets.
+
+The reference sends the same pickled query to every IndexServer over TCP and merges the
+pickled replies on the client's CPU (distributed_faiss/client.py:200-210, 265-310;
+rpc.py:120-131).  Inside one 8xB200 box this module replaces that with:
+
+    query  --(ncclBroadcast from the client rank)-->  every rank
+    every rank: libdfx search of its resident shards (+ local id -> caller id on device)
+    results --(ncclAllGather over NVLink/NVSwitch)--> [S, nq, k] on every rank
+    merge kernel K6 (float_maxheap_array_t semantics)  -> (D, I) on device
+
+One process per GPU (`IndexServer(rank=r)` <-> GPU r), `torch.distributed` for the plumbing.
+A rank may hold several shards (the 1/2/4-GPU points of the scaling curve hold 8/4/2 shards
+each); shards are numbered rank-major so the merge's "earlier shard wins ties" rule is the
+same for every GPU count.  The path has exactly one exchange step, as in the reference.
+
+`backend` abstracts the three device operations so that the world_size>1 host logic can be
+exercised on CPU with gloo (tests/test_spmd.py injects an oracle-backed backend); the
+default backend is CUDA-only and has no fallback.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+class CudaBackend:
+    """The product backend: everything runs in libdfx kernels on torch's current stream."""
+
+    name = "cuda"
+
+    def search(self, shard, x_t, k):
+        return shard.search_dev(x_t, k)
+
+    def map_ids(self, ids_t, table_t):
+        from . import engine
+
+        return engine.map_ids_dev(ids_t, table_t)
+
+    def merge(self, D_t, I_t, negate):
+        from . import engine
+
+        return engine.merge_dev(D_t, I_t, negate=negate)
+
+
+class ShardGroup:
+    """The set of shards of one index spread over the ranks of a process group.
+
+    shards     : this rank's engine objects (engine.GpuIndex), in global shard order
+    id_tables  : per local shard, int64 device tensor mapping shard-local id -> caller id
+                 (the integer-metadata convention of scripts/load_data.py:120-124), or None
+                 to return shard-local ids
+    Every rank must own the same number of shards.
+    """
+
+    def __init__(self, shards: Sequence, id_tables: Optional[Sequence] = None, group=None,
+                 backend=None, device=None):
+        self.shards = list(shards)
+        self.id_tables = list(id_tables) if id_tables is not None else [None] * len(self.shards)
+        assert len(self.id_tables) == len(self.shards)
+        self.group = group
+        self.backend = backend or CudaBackend()
+        self.world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+        self.rank = dist.get_rank(group) if self.world > 1 else 0
+        self.device = device if device is not None else (
+            torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu"))
+        self._pin_q = None
+        self._pin_D = None
+        self._pin_I = None
+
+    @property
+    def num_shards(self) -> int:
+        return len(self.shards) * self.world
+
+    def set_nprobe(self, nprobe: int):
+        for s in self.shards:
+            s.nprobe = nprobe
+
+    def get_ntotal(self) -> int:
+        n = torch.tensor([sum(s.ntotal for s in self.shards)], dtype=torch.int64, device=self.device)
+        if self.world > 1:
+            dist.all_reduce(n, group=self.group)
+        return int(n.item())
+
+    # ------------------------------------------------------------------ the hot path
+    def search(self, x_t: torch.Tensor, k: int, maximize: bool = False, src: int = 0):
+        """Collective.  x_t: float32 [nq, d] on this rank's device; the contents of rank `src`
+        are used (broadcast) -- the other ranks only need to pass a tensor of the same shape.
+        Returns (D [nq,k] float32 ascending -- negated scores when `maximize`, as the reference
+        returns them for metric "dot" --, I [nq,k] int64 caller ids, -1 = no result), on device,
+        identical on every rank."""
+        if self.world > 1:
+            dist.broadcast(x_t, src=src, group=self.group)
+        nq = x_t.shape[0]
+        S_loc = len(self.shards)
+        D_loc = torch.empty((S_loc, nq, k), dtype=torch.float32, device=x_t.device)
+        I_loc = torch.empty((S_loc, nq, k), dtype=torch.int64, device=x_t.device)
+        for j, shard in enumerate(self.shards):
+            Dj, Ij = self.backend.search(shard, x_t, k)
+            if self.id_tables[j] is not None:
+                Ij = self.backend.map_ids(Ij, self.id_tables[j])
+            D_loc[j].copy_(Dj)
+            I_loc[j].copy_(Ij)
+        if self.world > 1:
+            D_all = torch.empty((self.world * S_loc, nq, k), dtype=torch.float32, device=x_t.device)
+            I_all = torch.empty((self.world * S_loc, nq, k), dtype=torch.int64, device=x_t.device)
+            dist.all_gather_into_tensor(D_all, D_loc, group=self.group)
+            dist.all_gather_into_tensor(I_all, I_loc, group=self.group)
+        else:
+            D_all, I_all = D_loc, I_loc
+        return self.backend.merge(D_all, I_all, maximize)
+
+    def search_host(self, x: np.ndarray, k: int, maximize: bool = False, src: int = 0):
+        """End-to-end form with HOST buffers: pinned staging, H2D of the query batch, the
+        collective search, D2H of (D, I).  This is what IndexClient.search costs a caller."""
+        nq, d = x.shape
+        if self.device.type != "cuda":
+            D, I = self.search(torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32)), k, maximize, src)
+            return D.numpy(), I.numpy()
+        if self._pin_q is None or self._pin_q.shape != (nq, d):
+            self._pin_q = torch.empty((nq, d), dtype=torch.float32, pin_memory=True)
+        if self._pin_D is None or self._pin_D.shape != (nq, k):
+            self._pin_D = torch.empty((nq, k), dtype=torch.float32, pin_memory=True)
+            self._pin_I = torch.empty((nq, k), dtype=torch.int64, pin_memory=True)
+        self._pin_q.numpy()[...] = x
+        x_t = self._pin_q.to(self.device, non_blocking=True)
+        D, I = self.search(x_t, k, maximize, src)
+        self._pin_D.copy_(D, non_blocking=True)
+        self._pin_I.copy_(I, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return self._pin_D.numpy(), self._pin_I.numpy()
+
+
+def init_process_group_from_env(backend: Optional[str] = None):
+    """One process per GPU launched by torchrun: RANK / LOCAL_RANK / WORLD_SIZE / MASTER_*."""
+    import os
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if torch.cuda.is_available():
+        torch.cuda.set_device(local_rank % torch.cuda.device_count())
+    if world > 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29511")
+        kw = {}
+        if torch.cuda.is_available():
+            kw["device_id"] = torch.device("cuda", torch.cuda.current_device())
+        dist.init_process_group(backend or ("nccl" if torch.cuda.is_available() else "gloo"),
+                                rank=rank, world_size=world, **kw)
+    return rank, local_rank, world

@@ -125,6 +125,11 @@ int dfx_import_done(dfx_index *idx);
 /* statistics of the most recent search (device work, synchronises):
  * ndis = sum over (query, probed list) of the list length -- faiss's `ndis`. */
 int dfx_last_stats(dfx_index *idx, int64_t *ndis, int64_t *nq, int64_t *nprobe);
+/* per-kernel timing of the dominant kernel (the inverted-list scan): when enabled, every scan
+ * launch is bracketed by CUDA events on the launching stream; dfx_profile_read synchronises
+ * those events and returns the summed device time and the number of launches. */
+int dfx_profile_enable(dfx_index *idx, int on);
+int dfx_profile_read(dfx_index *idx, double *scan_ms, int64_t *scan_launches, int reset);
 /* number of kernel launches issued by this library since process start */
 int64_t dfx_launch_count(void);
 
