@@ -112,20 +112,25 @@ int dfx_train_dev(dfx_index* idx, int64_t n, const float* d_x, void* stream) {
     DFX_API_BEGIN
     std::lock_guard<std::mutex> lk(idx->mu);
     DeviceGuard g(idx->cfg.device);
+    idx->join_dev_if_other((cudaStream_t)stream);
     dfx_train_impl(idx, n, d_x, (cudaStream_t)stream);
+    idx->note_dev((cudaStream_t)stream);
     DFX_API_END
 }
 int dfx_add_dev(dfx_index* idx, int64_t n, const float* d_x, void* stream) {
     DFX_API_BEGIN
     std::lock_guard<std::mutex> lk(idx->mu);
     DeviceGuard g(idx->cfg.device);
+    idx->join_dev_if_other((cudaStream_t)stream);
     dfx_add_impl(idx, n, d_x, (cudaStream_t)stream);
+    idx->note_dev((cudaStream_t)stream);
     DFX_API_END
 }
 int dfx_train(dfx_index* idx, int64_t n, const float* x) {
     DFX_API_BEGIN
     std::lock_guard<std::mutex> lk(idx->mu);
     DeviceGuard g(idx->cfg.device);
+    idx->join_dev();
     DevBuf buf;
     buf.reserve((size_t)std::max<int64_t>(n, 1) * idx->cfg.d * 4);
     DFX_CUDA(cudaMemcpyAsync(buf.p, x, (size_t)n * idx->cfg.d * 4, cudaMemcpyHostToDevice, idx->stream));
@@ -137,6 +142,7 @@ int dfx_add(dfx_index* idx, int64_t n, const float* x) {
     DFX_API_BEGIN
     std::lock_guard<std::mutex> lk(idx->mu);
     DeviceGuard g(idx->cfg.device);
+    idx->join_dev();
     const int64_t chunk = 1 << 20;
     DevBuf buf;
     buf.reserve((size_t)std::min<int64_t>(std::max<int64_t>(n, 1), chunk) * idx->cfg.d * 4);
@@ -158,6 +164,7 @@ int dfx_finalize(dfx_index* idx, void* stream) {
     DFX_API_BEGIN
     std::lock_guard<std::mutex> lk(idx->mu);
     DeviceGuard g(idx->cfg.device);
+    idx->join_dev();
     cudaStream_t st = stream ? (cudaStream_t)stream : idx->stream;
     dfx_finalize_impl(idx, st);
     DFX_CUDA(cudaStreamSynchronize(st));
@@ -169,13 +176,16 @@ int dfx_search_dev(dfx_index* idx, int64_t nq, const float* d_x, int64_t k, floa
     DFX_API_BEGIN
     std::lock_guard<std::mutex> lk(idx->mu);
     DeviceGuard g(idx->cfg.device);
+    idx->join_dev_if_other((cudaStream_t)stream);
     dfx_search_impl(idx, nq, d_x, k, d_D, d_I, (cudaStream_t)stream);
+    idx->note_dev((cudaStream_t)stream);
     DFX_API_END
 }
 int dfx_search(dfx_index* idx, int64_t nq, const float* x, int64_t k, float* D, int64_t* I) {
     DFX_API_BEGIN
     std::lock_guard<std::mutex> lk(idx->mu);
     DeviceGuard g(idx->cfg.device);
+    idx->join_dev();
     if (nq <= 0) return 0;
     DFX_REQUIRE(k >= 1, "k must be >= 1");
     const int d = idx->cfg.d;
@@ -195,6 +205,7 @@ int dfx_reconstruct(dfx_index* idx, int64_t n, const int64_t* ids, float* out) {
     DFX_API_BEGIN
     std::lock_guard<std::mutex> lk(idx->mu);
     DeviceGuard g(idx->cfg.device);
+    idx->join_dev();
     if (n <= 0) return 0;
     DevBuf d_ids, d_out;
     d_ids.reserve((size_t)n * 8);
@@ -222,6 +233,7 @@ int dfx_get_centroids(dfx_index* idx, float* out) {
     DFX_REQUIRE(idx->is_ivf() && idx->trained, "index has no trained coarse quantizer");
     std::lock_guard<std::mutex> lk(idx->mu);
     DeviceGuard g(idx->cfg.device);
+    idx->join_dev();
     DFX_CUDA(cudaMemcpy(out, idx->centroids.p, (size_t)idx->cfg.nlist * idx->cfg.d * 4, cudaMemcpyDeviceToHost));
     DFX_API_END
 }
@@ -262,6 +274,7 @@ int dfx_last_stats(dfx_index* idx, int64_t* ndis, int64_t* nq, int64_t* nprobe) 
     DFX_API_BEGIN
     std::lock_guard<std::mutex> lk(idx->mu);
     DeviceGuard g(idx->cfg.device);
+    idx->join_dev();
     int64_t nd = 0;
     dfx_stats_impl(idx, &nd, idx->stream);
     if (ndis) *ndis = nd;
@@ -280,6 +293,7 @@ int dfx_profile_read(dfx_index* idx, double* scan_ms, int64_t* scan_launches, in
     DFX_API_BEGIN
     std::lock_guard<std::mutex> lk(idx->mu);
     DeviceGuard g(idx->cfg.device);
+    idx->join_dev();
     double ms = 0;
     for (size_t i = 0; i < idx->prof_used; i++) {
         DFX_CUDA(cudaEventSynchronize(idx->prof_events[i].second));
@@ -308,6 +322,7 @@ int dfx_get_array(dfx_index* idx, const char* name, void* out, int64_t max_bytes
     DFX_API_BEGIN
     std::lock_guard<std::mutex> lk(idx->mu);
     DeviceGuard g(idx->cfg.device);
+    idx->join_dev();
     if (idx->n_pending > 0) dfx_finalize_impl(idx, idx->stream);
     std::string n(name);
     const int64_t nt = idx->n_sorted, nlist = idx->cfg.nlist, d = idx->cfg.d;
@@ -340,6 +355,7 @@ int dfx_set_array(dfx_index* idx, const char* name, const void* in, int64_t nbyt
     DFX_API_BEGIN
     std::lock_guard<std::mutex> lk(idx->mu);
     DeviceGuard g(idx->cfg.device);
+    idx->join_dev();
     std::string n(name);
     const int64_t nlist = idx->cfg.nlist, d = idx->cfg.d;
     auto upload = [&](DevBuf& b, int64_t bytes) {
@@ -398,6 +414,7 @@ int dfx_import_done(dfx_index* idx) {
     DFX_API_BEGIN
     std::lock_guard<std::mutex> lk(idx->mu);
     DeviceGuard g(idx->cfg.device);
+    idx->join_dev();
     if (idx->is_ivf()) {
         DFX_REQUIRE(idx->centroids.p && idx->list_off.p, "import: centroids and list_off are required");
         if (idx->cfg.kind == DFX_IVF_PQ) {
@@ -449,9 +466,11 @@ __global__ void synth_rows_kernel(dfx_synth p, const float* __restrict__ A, int6
     if (r >= n) return;
     const int64_t row = rows ? rows[r] : row0 + r;
     const uint64_t cluster = (uint64_t)(row % p.nclusters);
+    const uint64_t zkey = p.ngroups > 0 ? (uint64_t)(row % p.ngroups) : (uint64_t)row;
     if (threadIdx.x < p.r) {
-        float z = hash_normal(hash4(p.seed, 2, (uint64_t)row, threadIdx.x));
-        z = fminf(4.f, fmaxf(-4.f, z));
+        float z = hash_normal(hash4(p.seed, 2, zkey, threadIdx.x));
+        z = p.sigma * fminf(4.f, fmaxf(-4.f, z));
+        if (p.delta > 0.f) z += p.delta * hash_normal(hash4(p.seed, 5, (uint64_t)row, threadIdx.x));
         s_z[threadIdx.x] = z;
     }
     __syncthreads();
@@ -459,7 +478,8 @@ __global__ void synth_rows_kernel(dfx_synth p, const float* __restrict__ A, int6
         float mu = hash_normal(hash4(p.seed, 1, cluster, k));
         float az = 0.f;
         for (int j = 0; j < p.r; j++) az += A[k * p.r + j] * s_z[j];
-        float v = mu + p.sigma * az;
+        float v = mu + az;
+        if (p.eps > 0.f) v += p.eps * hash_normal(hash4(p.seed, 4, (uint64_t)row, k));
         if (p.sigma_q > 0.f && noise_stream)
             v += p.sigma_q * hash_normal(hash4(p.seed, noise_stream, (uint64_t)row, k));
         out[r * p.d + k] = v;
@@ -507,6 +527,7 @@ int dfx_synth_rows_dev(const dfx_synth* p, const float* d_A, int64_t row0, const
     DFX_API_BEGIN
     if (n <= 0) return 0;
     DFX_REQUIRE(p->nclusters >= 1, "synth: nclusters >= 1");
+    DFX_REQUIRE(p->ngroups == 0 || p->ngroups % p->nclusters == 0, "synth: ngroups must be a multiple of nclusters");
     DFX_LAUNCH(synth_rows_kernel, (unsigned)n, 128, 0, (cudaStream_t)stream, *p, d_A, row0, d_rows, n,
                noise_stream, d_out);
     DFX_API_END

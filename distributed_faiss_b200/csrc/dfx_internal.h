@@ -45,6 +45,24 @@ struct dfx_index {
     bool last_keys_valid = false;
 
     cudaStream_t stream = nullptr;  // used by the host-pointer entry points
+    // stream of the most recent *_dev call; host-pointer entry points (which run on `stream`,
+    // a non-blocking stream) wait for it first so that the two never race
+    cudaStream_t last_dev_stream = nullptr;
+    bool dev_work_pending = false;
+    void note_dev(cudaStream_t st) {
+        last_dev_stream = st;
+        dev_work_pending = true;
+    }
+    // a *_dev call on a different stream than the previous one: order them
+    void join_dev_if_other(cudaStream_t st) {
+        if (dev_work_pending && st != last_dev_stream) join_dev();
+    }
+    void join_dev() {
+        if (dev_work_pending) {
+            cudaStreamSynchronize(last_dev_stream);
+            dev_work_pending = false;
+        }
+    }
     std::mutex mu;
 
     size_t row_bytes() const {

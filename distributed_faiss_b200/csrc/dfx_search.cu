@@ -231,13 +231,29 @@ pq_prep_kernel(const float* __restrict__ Q, int d, int M, int ksub, int dsub,
 struct WarpTopK {
     uint64_t* buf;
     int cap, k, cnt;
-    float thr;
+    float thr;         // value of the current k-th best (+inf until k candidates are held)
+    uint32_t thr_sec;  // its secondary key: an equal value is only admitted with a smaller one
     __device__ __forceinline__ void init(uint64_t* b, int cap_, int k_) {
         buf = b;
         cap = cap_;
         k = k_;
         cnt = 0;
         thr = __int_as_float(0x7f800000);  // +inf
+        thr_sec = DFX_SEC_NONE;
+    }
+    // does (v, sec) beat the current k-th best?  `sec` is fetched lazily: only on a value tie
+    template <class SecFn>
+    __device__ __forceinline__ bool admits(float v, SecFn sec_of, uint32_t& sec) const {
+        v = v + 0.0f;
+        if (v < thr) {
+            sec = sec_of();
+            return true;
+        }
+        if (v == thr) {
+            sec = sec_of();
+            return sec < thr_sec;
+        }
+        return false;
     }
     __device__ __forceinline__ void sort_and_cut() {
         const int lane = threadIdx.x & 31;
@@ -259,7 +275,11 @@ struct WarpTopK {
             }
         }
         if (cnt > k) cnt = k;
-        if (cnt == k) thr = dfx_key2f((uint32_t)(buf[k - 1] >> 32));
+        if (cnt == k) {
+            const uint64_t kth = buf[k - 1];
+            thr = dfx_key2f((uint32_t)(kth >> 32));
+            thr_sec = (uint32_t)kth;
+        }
         __syncwarp();
     }
     // each lane may contribute one candidate (want = lane has one)
@@ -361,9 +381,8 @@ scan_pq_kernel(const float* __restrict__ lut, const float* __restrict__ dis0,
                 const float S = (a0 + a1) + (a2 + a3);
                 v = d0 + (__ldg(tvals + i) + S);
             }
-            const bool want = valid && (v <= wt.thr);
             uint32_t sec = 0;
-            if (want) sec = (uint32_t)__ldg(ids + i);
+            const bool want = valid && wt.admits(v, [&] { return (uint32_t)__ldg(ids + i); }, sec);
             wt.push_lanes(want, v, sec);
         }
     }
@@ -458,7 +477,9 @@ scan_rows_kernel(const float* __restrict__ Q, int d, const float* __restrict__ c
                 const int64_t i = base + u;
                 float v = dfx_warp_butterfly(acc[u]);
                 if (MODE == 0) v = -v;
-                if (i < end && v <= wt.thr) wt.push_uniform(v, (uint32_t)__ldg(ids + i));
+                uint32_t sec = 0;
+                if (i < end && wt.admits(v, [&] { return (uint32_t)__ldg(ids + i); }, sec))
+                    wt.push_uniform(v, sec);
             }
         }
     }

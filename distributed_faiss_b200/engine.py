@@ -45,7 +45,8 @@ class DfxCfg(C.Structure):
 
 class DfxSynth(C.Structure):
     _fields_ = [("seed", C.c_uint64), ("d", C.c_int32), ("r", C.c_int32), ("nclusters", C.c_int64),
-                ("sigma", C.c_float), ("sigma_q", C.c_float)]
+                ("ngroups", C.c_int64), ("sigma", C.c_float), ("eps", C.c_float), ("sigma_q", C.c_float),
+                ("delta", C.c_float)]
 
 
 _lib = None
@@ -336,10 +337,11 @@ def map_ids_dev(ids_t, table_t, out_t=None):
 class Synth:
     """Device-side generator of SURVEY.md 8(d): clustered, low intrinsic dimension, counter based."""
 
-    def __init__(self, seed, d, r, nclusters, sigma, sigma_q=0.0):
+    def __init__(self, seed, d, r, nclusters, sigma, sigma_q=0.0, ngroups=0, eps=0.0, delta=0.0):
         import torch
 
-        self.p = DfxSynth(int(seed), int(d), int(r), int(nclusters), float(sigma), float(sigma_q))
+        self.p = DfxSynth(int(seed), int(d), int(r), int(nclusters), int(ngroups), float(sigma), float(eps),
+                          float(sigma_q), float(delta))
         self._A = C.c_void_p()
         st = torch.cuda.current_stream().cuda_stream
         _check(lib().dfx_synth_init(C.byref(self.p), C.byref(self._A), C.c_void_p(st)))

@@ -133,18 +133,24 @@ int dfx_profile_read(dfx_index *idx, double *scan_ms, int64_t *scan_launches, in
 /* number of kernel launches issued by this library since process start */
 int64_t dfx_launch_count(void);
 
-/* ---- synthetic data on device (bench harness; SURVEY.md 8d generator) ----
- * x_i = mu_{c(i)} + sigma * A z_i : C cluster centres ~ N(0,I_d), latent z ~ N(0,I_r) clipped
- * to |z|<=4, c(i) = i mod C, A: d x r with orthonormal columns.  Counter-based: any row
- * is regenerable anywhere from (seed, row).  rows: optional explicit row ids (else
- * row0 .. row0+n-1).  noise: isotropic sigma_q * N(0,I_d) added on top (for queries). */
+/* ---- synthetic data on device (bench harness; SURVEY.md 8d generator, see DESIGN.md) ----
+ * x_i = mu_{c(i)} + A (sigma * z_{g(i)} + delta * w_i) + eps * n_i
+ *   C cluster centres mu_c ~ N(0, I_d);  c(i) = i mod C
+ *   G groups ("near-duplicate" micro-clusters), g(i) = i mod G (G multiple of C; G = 0: one
+ *   group per row); latent z_g ~ N(0, I_r) clipped to |z| <= 4;  A: d x r, orthonormal columns
+ *   w_i ~ N(0, I_r), n_i ~ N(0, I_d) per row.
+ * Counter-based: any row is regenerable anywhere from (seed, row).  rows: optional explicit row
+ * ids (else row0 .. row0+n-1).  noise_stream != 0 adds sigma_q * N(0, I_d) (queries). */
 typedef struct dfx_synth {
     uint64_t seed;
     int32_t d;
-    int32_t r;        /* intrinsic dimension */
+    int32_t r;        /* intrinsic dimension of the cluster-level structure */
     int64_t nclusters;
+    int64_t ngroups;
     float sigma;
+    float eps;
     float sigma_q;
+    float delta;
 } dfx_synth;
 int dfx_synth_init(const dfx_synth *p, float **d_A_out /* device [d,r], caller frees with dfx_free */,
                    void *stream);

@@ -276,3 +276,41 @@ def test_gpu_training_quality():
     assert eg < 1.25 * eo + 1e-6, (eg, eo)
     lens = np.diff(g.get_array("list_off"))
     assert lens.sum() == n and (lens > 0).sum() >= nlist // 2
+
+
+def test_device_pointer_path_matches_host_path():
+    """train_dev/add_dev/finalize/search_dev on torch's stream (the NCCL data plane uses these)
+    must give the same shard and the same answers as the host-buffer entry points, including
+    when host- and device-stream calls are interleaved (regression: cross-stream race)."""
+    import torch
+    from oracle import oracle as O
+
+    E = _engine()
+    rs = np.random.RandomState(11)
+    d, nlist, M, n = 128, 64, 32, 50_000
+    xb = clustered(rs, n, d, ncl=80)
+    xq = xb[:40] + 0.01 * rs.randn(40, d).astype(np.float32)
+    g = E.GpuIndex(E.KIND_IVF_PQ, d, L2, nlist=nlist, pq_m=M)
+    xb_t = torch.from_numpy(xb).cuda()
+    g.train_dev(xb_t[:20000].contiguous())
+    for i0 in range(0, n, 12500):
+        g.add_dev(xb_t[i0:i0 + 12500].contiguous())
+    g.finalize()  # host-side call right behind asynchronous device-stream work
+    assert g.ntotal == n
+    o = O.OracleIVFPQ(d, nlist, M, 8, coarse_metric=L2)
+    o.set_state(g.get_state())
+    # the shard built through the device path holds what the oracle would have built from the
+    # same trained state: same assignment, same codes
+    o2 = O.OracleIVFPQ(d, nlist, M, 8, coarse_metric=L2)
+    o2.centroids, o2.codebooks, o2.is_trained = o.centroids, o.codebooks, True
+    o2.add(xb)
+    assert np.array_equal(o2.list_off, o.list_off)
+    assert np.array_equal(o2.ids, o.ids) and np.array_equal(o2.codes, o.codes)
+    assert np.array_equal(o2.tvals, o.tvals)
+    g.nprobe = 8; o.nprobe = 8
+    D_t, I_t = g.search_dev(torch.from_numpy(xq).cuda(), 10)
+    stats = g.last_stats()  # host-side call behind device-stream work
+    Do, Io = o.search(xq, 10)
+    _assert_same(D_t.cpu().numpy(), I_t.cpu().numpy(), Do, Io, "search_dev")
+    assert stats["ndis"] == o.last_ndis
+    _assert_same(*g.search(xq, 10), Do, Io, "host search after device search")
