@@ -104,6 +104,7 @@ int dfx_set_param(dfx_index* idx, const char* name, double value) {
     if (n == "kmeans_niter") idx->kmeans_niter = (int)value;
     else if (n == "max_points_per_centroid") idx->max_points_per_centroid = (int)value;
     else if (n == "train_seed") idx->train_seed = (uint64_t)value;
+    else if (n == "tensor_cores") idx->tc_enabled = value != 0;
     else throw DfxError{"unknown parameter " + n};
     DFX_API_END
 }
@@ -421,6 +422,7 @@ int dfx_import_done(dfx_index* idx) {
             DFX_REQUIRE(idx->codebooks.p, "import: codebooks are required");
             dfx_compute_tvals_sorted(idx, idx->stream);  // K7 recomputes the per-vector term
         }
+        dfx_tc_prepare_centroids(idx, idx->stream);
         DFX_CUDA(cudaStreamSynchronize(idx->stream));
     }
     idx->trained = true;

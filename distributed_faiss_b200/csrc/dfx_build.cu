@@ -190,6 +190,10 @@ void dfx_assign_impl(dfx_index* idx, const float* d_cent, const float* d_cnorm, 
                      int metric, int d, int64_t n, const float* d_x, int32_t* d_assign,
                      cudaStream_t st) {
     if (n <= 0) return;
+    if (idx->tc_enabled && dfx_tc_supported(d) && nlist >= 1024) {
+        dfx_tc_assign(idx, d, d_cent, d_cnorm, nlist, metric, n, d_x, d_assign, st);
+        return;
+    }
     idx->w_best.reserve((size_t)n * 8);
     dfx_launch_assign_fused(d_x, n, d_cent, d_cnorm, nlist, d, metric,
                             idx->w_best.as<unsigned long long>(), d_assign, st);
@@ -308,6 +312,7 @@ void dfx_train_impl(dfx_index* idx, int64_t n, const float* d_x, cudaStream_t st
     idx->cnorm.reserve((size_t)nlist * 4);
     kmeans_device(idx, d, nt, xt, nlist, niter, seed, idx->centroids.as<float>(), st);
     dfx_launch_row_norms(idx->centroids.as<float>(), nlist, d, idx->cnorm.as<float>(), st);
+    dfx_tc_prepare_centroids(idx, st);
 
     if (kind == DFX_IVF_PQ) {
         const int M = idx->M, ksub = idx->ksub, dsub = idx->dsub;

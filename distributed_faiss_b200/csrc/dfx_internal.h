@@ -35,6 +35,11 @@ struct dfx_index {
     int max_points_per_centroid = 256;  // faiss Clustering default
     uint64_t train_seed = 1234;       // faiss Clustering default seed
 
+    // tensor-core coarse quantizer (dfx_tc.cu): bf16 hi/lo planes and screening workspace
+    DevBuf tc_cent, tc_cent_tmp, tc_q, tc_gmin, tc_groups, tc_cand;
+    bool tc_ready = false;
+    bool tc_enabled = true;
+
     // scan-kernel profiling (dfx_profile_enable)
     bool prof_on = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
@@ -95,6 +100,17 @@ void dfx_merge_impl(int64_t S, int64_t nq, int64_t k, const float* d_D, const in
 void dfx_map_ids_impl(int64_t n, const int64_t* d_ids, const int64_t* d_table, int64_t* d_out,
                       cudaStream_t st);
 void dfx_stats_impl(dfx_index* idx, int64_t* ndis, cudaStream_t st);
+
+void dfx_launch_select_comp(const uint64_t* comp, int64_t nrows, int n, int64_t ld, int k, int32_t* keys,
+                            cudaStream_t st);
+
+// ---- dfx_tc.cu
+bool dfx_tc_supported(int d);
+void dfx_tc_prepare_centroids(dfx_index* idx, cudaStream_t st);
+void dfx_tc_coarse_search(dfx_index* idx, const float* d_x, int64_t nq, int nprobe, int32_t* keys,
+                          cudaStream_t st);
+void dfx_tc_assign(dfx_index* idx, int d, const float* d_cent, const float* d_cnorm, int64_t nlist, int metric,
+                   int64_t n, const float* d_x, int32_t* d_assign, cudaStream_t st);
 
 // ---- dfx_build.cu
 void dfx_train_impl(dfx_index* idx, int64_t n, const float* d_x, cudaStream_t st);

@@ -177,6 +177,13 @@ void dfx_launch_select_cols(const float* vals, int64_t nrows, int n, int64_t ld,
     dfx_launch_select<256>(ldr, wr, nrows, n, k, st);
 }
 
+void dfx_launch_select_comp(const uint64_t* comp, int64_t nrows, int n, int64_t ld, int k, int32_t* keys,
+                            cudaStream_t st) {
+    CompLoader ldr{comp, ld};
+    KeysWriter wr{keys, nullptr, nullptr, 0, k};
+    dfx_launch_select<256>(ldr, wr, nrows, n, k, st);
+}
+
 // =====================================================================================
 // K3: pq_prep.  lut[q][m][j] = -2 * ip_seq(q_m, P[m][j]);  dis0[q][p] = warp-dot ||q - c||^2
 // =====================================================================================
@@ -652,7 +659,6 @@ void dfx_search_impl(dfx_index* idx, int64_t nq, const float* d_x, int64_t k64, 
     const int KP = dfx_next_pow2(k < 32 ? 32 : k);
     const int cap = 2 * KP;
 
-    idx->w_vals.reserve((size_t)QC * nlist * 4);
     idx->w_keys.reserve((size_t)nq * nprobe * 4);
     int32_t* keys_all = idx->w_keys.as<int32_t>();
 
@@ -660,11 +666,16 @@ void dfx_search_impl(dfx_index* idx, int64_t nq, const float* d_x, int64_t k64, 
         const int64_t qc = (nq - q0 < QC) ? (nq - q0) : QC;
         const float* xq = d_x + q0 * d;
         int32_t* keys = keys_all + q0 * nprobe;
-        // K1: coarse quantizer
-        dfx_launch_gemm_values(xq, qc, idx->centroids.as<float>(), idx->cnorm.as<float>(), nlist, d,
-                               cmetric, idx->w_vals.as<float>(), nlist, st);
-        dfx_launch_select_cols(idx->w_vals.as<float>(), qc, (int)nlist, nlist, nprobe, 0, keys,
-                               nullptr, nullptr, 0, st);
+        // K1: coarse quantizer -- tensor cores (screen) + canonical fp32 (decide), or plain FFMA
+        if (idx->tc_enabled && idx->tc_ready && nlist >= 1024 && nprobe <= 512) {
+            dfx_tc_coarse_search(idx, xq, qc, nprobe, keys, st);
+        } else {
+            idx->w_vals.reserve((size_t)QC * nlist * 4);
+            dfx_launch_gemm_values(xq, qc, idx->centroids.as<float>(), idx->cnorm.as<float>(), nlist, d,
+                                   cmetric, idx->w_vals.as<float>(), nlist, st);
+            dfx_launch_select_cols(idx->w_vals.as<float>(), qc, (int)nlist, nlist, nprobe, 0, keys,
+                                   nullptr, nullptr, 0, st);
+        }
         const int G = choose_group(qc, nprobe);
         const int ngroups = (nprobe + G - 1) / G;
         idx->w_part.reserve((size_t)qc * ngroups * k * 8);

@@ -1,0 +1,522 @@
+// dfx_tc.cu -- K1: the coarse quantizer on 5th-generation tensor cores (tcgen05 + TMEM + TMA).
+//
+// Replaces the dense query x centroid contraction inside `quantizer.search(nq, x, nprobe)`
+// (faiss IndexIVF::search, reached from reference distributed_faiss/index.py:257) and
+// `quantizer.assign` (IndexIVF::add, index.py:425).
+//
+// Scheme ("screen on tensor cores, decide in canonical fp32"):
+//   1. fp32 operands are split into bf16 hi + lo planes; q.c ~= qh.ch + ql.ch + qh.cl is
+//      accumulated in fp32 in TMEM by tcgen05.mma (relative error ~1e-6, the ql.cl term
+//      ~2^-18 is dropped).
+//   2. the epilogue turns each 128x128 accumulator tile into ranking values
+//      (L2: |c|^2 - 2 q.c, IP: -q.c) and keeps only the MINIMUM of every group of 32
+//      consecutive centroids -> gmin[nq][nlist/32]  (32x less traffic than the full matrix).
+//   3. the G = nprobe + margin groups with the smallest minima are selected exactly
+//      (dfx_select.cuh).  Every true top-nprobe centroid lies in one of the nprobe groups
+//      with the smallest group minimum; `margin` absorbs the 1e-6 screening error.
+//   4. the G*32 candidate centroids are re-evaluated in the CANONICAL fp32 order
+//      (seq-k FMA, identical to oracle/dfx_oracle.c) and the final top-nprobe / argmin is
+//      taken on those exact values -> the probe lists are bit-identical to the oracle's.
+//
+// One CTA = 6 warps: warp 0 TMA producer, warp 1 TMEM allocator + single-thread MMA issuer,
+// warps 2..5 epilogue (one TMEM lane == one query row per thread).  A (query planes) stays
+// resident in shared memory, B (centroid planes) streams through a ring of 16 KB stages, two
+// TMEM accumulator buffers overlap the epilogue of tile i with the MMAs of tile i+1.
+#include "dfx_internal.h"
+#include "dfx_select.cuh"
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tm, uint64_t* bar, int c0,
+                                            int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"((uint64_t)tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_alloc(uint32_t* smem_dst, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)),
+                 "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tc_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                     smem_u32(bar))
+                 : "memory");
+}
+// 32 consecutive fp32 columns of this thread's TMEM lane
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (rows of 128 B, 8-row atoms of 1024 B)
+__device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3ffffu) >> 4);  // start address, 16-byte units
+    d |= (uint64_t)(1024u >> 4) << 32;             // stride byte offset between 8-row atoms
+    d |= (uint64_t)1 << 46;                        // descriptor version (sm_100)
+    d |= (uint64_t)2 << 61;                        // SWIZZLE_128B
+    return d;
+}
+
+// instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=128
+static constexpr uint32_t TC_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+
+// ------------------------------------------------------------------ the kernel
+namespace tc {
+constexpr int TILE = 128;           // rows of A and of B per tile
+constexpr int KATOM = 64;           // bf16 elements per 128-byte swizzle row
+constexpr int ATOM_BYTES = TILE * KATOM * 2;  // 16 KB
+constexpr int NSTAGE = 8;
+constexpr int THREADS = 192;
+constexpr int TMEM_COLS = 256;      // two 128-column accumulator buffers
+struct Smem {
+    // offsets inside the 1024-aligned dynamic shared memory block
+    static constexpr int A = 0;                                   // [plane hi/lo][katom] x 16 KB
+    static constexpr int B(int katoms) { return 2 * katoms * ATOM_BYTES; }
+    static constexpr int BARS(int katoms) { return B(katoms) + NSTAGE * ATOM_BYTES; }
+    static constexpr int total(int katoms) { return BARS(katoms) + 512 + 2 * TILE * 4; }
+};
+}  // namespace tc
+
+// tmQ: bf16 [2*nq_pad, d]  (rows [0,nq_pad) = hi plane, [nq_pad, 2 nq_pad) = lo plane)
+// tmC: bf16 [2*nl_pad, d]
+// gmin: float [nq][ng], ng = nl_pad/32
+template <int KATOMS>
+__global__ void __launch_bounds__(tc::THREADS, 1)
+tc_coarse_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmC, int nq,
+                 int nq_pad, int nlist, int nl_pad, const float* __restrict__ cnorm, int metric, int ctiles_per_cta,
+                 float* __restrict__ gmin, int ng) {
+    using namespace tc;
+    extern __shared__ unsigned char smem_raw_tc[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>(
+        (reinterpret_cast<uintptr_t>(smem_raw_tc) + 1023) & ~(uintptr_t)1023);  // SWIZZLE_128B atoms
+    unsigned char* sA = smem + Smem::A;
+    unsigned char* sB = smem + Smem::B(KATOMS);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Smem::BARS(KATOMS));
+    uint64_t* full = bars;                 // [NSTAGE]
+    uint64_t* empty = bars + NSTAGE;       // [NSTAGE]
+    uint64_t* a_full = bars + 2 * NSTAGE;  // [1]
+    uint64_t* t_full = a_full + 1;         // [2]
+    uint64_t* t_empty = t_full + 2;        // [2]
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(t_empty + 2);
+    float* s_cn = reinterpret_cast<float*>(smem + Smem::BARS(KATOMS) + 512);  // [2][TILE]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int qt = blockIdx.y;
+    const int ctiles = nl_pad / TILE;
+    const int ct0 = blockIdx.x * ctiles_per_cta;
+    const int ct1 = min(ctiles, ct0 + ctiles_per_cta);
+    const int ntiles = ct1 - ct0;
+    if (ntiles <= 0) return;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < NSTAGE; i++) {
+            mbar_init(&full[i], 1);
+            mbar_init(&empty[i], 1);
+        }
+        mbar_init(a_full, 1);
+        for (int b = 0; b < 2; b++) {
+            mbar_init(&t_full[b], 1);
+            mbar_init(&t_empty[b], 4);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) tc_alloc(tmem_ptr, TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    constexpr int STAGES_PER_TILE = 2 * KATOMS;  // ch atoms then cl atoms
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            mbar_expect_tx(a_full, 2 * KATOMS * ATOM_BYTES);
+            for (int pl = 0; pl < 2; pl++)
+                for (int ka = 0; ka < KATOMS; ka++)
+                    tma_load_2d(sA + (pl * KATOMS + ka) * ATOM_BYTES, &tmQ, a_full, ka * KATOM,
+                                pl * nq_pad + qt * TILE);
+            int stage = 0, phase = 0;
+            for (int t = 0; t < ntiles; t++) {
+                const int crow = (ct0 + t) * TILE;
+                for (int s = 0; s < STAGES_PER_TILE; s++) {
+                    const int pl = s / KATOMS, ka = s % KATOMS;
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    mbar_expect_tx(&full[stage], ATOM_BYTES);
+                    tma_load_2d(sB + stage * ATOM_BYTES, &tmC, &full[stage], ka * KATOM, pl * nl_pad + crow);
+                    if (++stage == NSTAGE) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (one thread) =====================
+        if (lane == 0) {
+            mbar_wait(a_full, 0);
+            tc_fence_after();
+            int stage = 0, phase = 0;
+            const uint32_t a_base = smem_u32(sA);
+            const uint32_t b_base = smem_u32(sB);
+            for (int t = 0; t < ntiles; t++) {
+                const int buf = t & 1;
+                mbar_wait(&t_empty[buf], ((t >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + buf * TILE;
+                for (int s = 0; s < STAGES_PER_TILE; s++) {
+                    const int pl = s / KATOMS, ka = s % KATOMS;
+                    mbar_wait(&full[stage], phase);
+                    tc_fence_after();
+                    const uint32_t b_addr = b_base + stage * ATOM_BYTES;
+                    const uint32_t ah_addr = a_base + (0 * KATOMS + ka) * ATOM_BYTES;
+                    const uint32_t al_addr = a_base + (1 * KATOMS + ka) * ATOM_BYTES;
+#pragma unroll
+                    for (int kk = 0; kk < KATOM / 16; kk++) {  // UMMA_K = 16 bf16 = 32 bytes
+                        const uint64_t bd = make_kmajor_sw128_desc(b_addr + kk * 32);
+                        // qh . (ch | cl)
+                        tc_mma_bf16(d_tmem, make_kmajor_sw128_desc(ah_addr + kk * 32), bd, TC_IDESC,
+                                    (s > 0 || kk > 0) ? 1u : 0u);
+                        // ql . ch
+                        if (pl == 0) tc_mma_bf16(d_tmem, make_kmajor_sw128_desc(al_addr + kk * 32), bd, TC_IDESC, 1u);
+                    }
+                    tc_commit(&empty[stage]);  // frees the stage once these MMAs have read it
+                    if (++stage == NSTAGE) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+                tc_commit(&t_full[buf]);  // accumulator of this tile complete
+            }
+        }
+    } else {
+        // ===================== epilogue: TMEM -> group minima =====================
+        const int quad = warp & 3;             // TMEM lane quadrant this warp may access
+        const int row = quad * 32 + lane;      // query row inside the tile == TMEM lane
+        const int64_t grow = (int64_t)qt * TILE + row;
+        const int et = threadIdx.x - 64;       // 0..127
+        for (int t = 0; t < ntiles; t++) {
+            const int buf = t & 1;
+            const int col0 = (ct0 + t) * TILE;
+            {
+                const int c = col0 + et;
+                float cn = 0.f;
+                if (metric == DFX_METRIC_L2 && c < nlist) cn = cnorm[c];
+                s_cn[buf * TILE + et] = (c < nlist) ? cn : __int_as_float(0x7f800000);
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            mbar_wait(&t_full[buf], (t >> 1) & 1);
+            tc_fence_after();
+            float gm[4];
+#pragma unroll
+            for (int ch = 0; ch < 4; ch++) {
+                uint32_t r[32];
+                tc_ld32(tmem_base + buf * TILE + ch * 32 + ((uint32_t)(quad * 32) << 16), r);
+                float m = __int_as_float(0x7f800000);
+#pragma unroll
+                for (int j = 0; j < 32; j++) {
+                    const float ip = __uint_as_float(r[j]);
+                    const float cn = s_cn[buf * TILE + ch * 32 + j];
+                    const float v = (metric == DFX_METRIC_IP) ? (cn - ip) : fmaf(-2.f, ip, cn);
+                    m = fminf(m, v);
+                }
+                gm[ch] = m;
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&t_empty[buf]);
+            if (grow < nq) {
+                float4 o = make_float4(gm[0], gm[1], gm[2], gm[3]);
+                *reinterpret_cast<float4*>(gmin + grow * ng + (col0 >> 5)) = o;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tc_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+// ------------------------------------------------------------------ helpers around it
+// fp32 [n, d] -> bf16 hi/lo planes [2][n_pad][d] (rows >= n zero filled)
+__global__ void split_bf16_kernel(const float* __restrict__ x, int64_t n, int64_t n_pad, int d,
+                                  __nv_bfloat16* __restrict__ out) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_pad * d) return;
+    int64_t i = t / d;
+    float v = (i < n) ? x[t] : 0.f;
+    __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+    out[t] = hi;
+    out[n_pad * d + t] = lo;
+}
+
+// the G smallest group minima of a row, G <= 8: one warp per row, G rounds of warp arg-min
+template <int G>
+__global__ void topg_small_kernel(const float* __restrict__ gmin, int64_t nq, int ng,
+                                  int32_t* __restrict__ groups) {
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= nq) return;
+    const float* g = gmin + row * ng;
+    uint64_t taken[G];
+#pragma unroll
+    for (int r = 0; r < G; r++) taken[r] = DFX_COMP_NONE;
+#pragma unroll
+    for (int r = 0; r < G; r++) {
+        uint64_t best = DFX_COMP_NONE;
+        const uint64_t prev = (r == 0) ? 0 : taken[r - 1];
+        for (int j = lane; j < ng; j += 32) {
+            uint64_t c = dfx_comp(g[j], (uint32_t)j);
+            // composites are unique: the r-th smallest is the smallest one above the (r-1)-th
+            if ((r == 0 || c > prev) && c < best) best = c;
+        }
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) {
+            uint64_t o = __shfl_xor_sync(0xffffffffu, best, off);
+            best = o < best ? o : best;
+        }
+        taken[r] = best;
+        if (lane == 0) groups[row * G + r] = (best == DFX_COMP_NONE) ? -1 : (int32_t)(uint32_t)best;
+    }
+}
+
+// exact canonical fp32 values of the candidate centroids: out[row][c] = comp(value, centroid)
+// ARGMIN: instead write the arg-min centroid of the row to assign[row]
+template <bool ARGMIN>
+__global__ void __launch_bounds__(128)
+rerank_kernel(const float* __restrict__ Q, int d, const float* __restrict__ cent, const float* __restrict__ cnorm,
+              int64_t nlist, int metric, const int32_t* __restrict__ groups, int G, uint64_t* __restrict__ out,
+              int32_t* __restrict__ assign) {
+    extern __shared__ float s_q[];
+    __shared__ unsigned long long s_best[4];
+    const int64_t row = blockIdx.x;
+    for (int i = threadIdx.x; i < d; i += 128) s_q[i] = Q[row * d + i];
+    __syncthreads();
+    unsigned long long best = DFX_COMP_NONE;
+    const int ncand = G * 32;
+    for (int c = threadIdx.x; c < ncand; c += 128) {
+        const int gid = groups[row * G + (c >> 5)];
+        const int64_t col = (int64_t)gid * 32 + (c & 31);
+        unsigned long long comp = DFX_COMP_NONE;
+        if (gid >= 0 && col < nlist) {
+            const float* x = cent + col * d;
+            float acc = 0.f;
+            for (int k = 0; k < d; k += 4) {
+                const float4 xv = *reinterpret_cast<const float4*>(x + k);
+                acc = __fmaf_rn(s_q[k + 0], xv.x, acc);
+                acc = __fmaf_rn(s_q[k + 1], xv.y, acc);
+                acc = __fmaf_rn(s_q[k + 2], xv.z, acc);
+                acc = __fmaf_rn(s_q[k + 3], xv.w, acc);
+            }
+            const float v = (metric == DFX_METRIC_IP) ? -acc : __fmaf_rn(-2.f, acc, cnorm[col]);
+            comp = dfx_comp(v, (uint32_t)col);
+        }
+        if (ARGMIN) best = comp < best ? comp : best;
+        else out[row * ncand + c] = comp;
+    }
+    if (ARGMIN) {
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) {
+            unsigned long long o = __shfl_xor_sync(0xffffffffu, best, off);
+            best = o < best ? o : best;
+        }
+        if ((threadIdx.x & 31) == 0) s_best[threadIdx.x >> 5] = best;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int w = 1; w < 4; w++) best = s_best[w] < best ? s_best[w] : best;
+            assign[row] = (best == DFX_COMP_NONE) ? -1 : (int32_t)(uint32_t)best;
+        }
+    }
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn() {
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        DFX_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres));
+        DFX_REQUIRE(p != nullptr && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not available");
+        fn = (PFN_encodeTiled)p;
+    }
+    return fn;
+}
+
+// bf16 matrix [rows, d] row-major, box = 128 rows x 64 columns, 128-byte swizzle
+static void make_tmap(CUtensorMap* tm, const void* base, int64_t rows, int d) {
+    cuuint64_t gdim[2] = {(cuuint64_t)d, (cuuint64_t)rows};
+    cuuint64_t gstr[1] = {(cuuint64_t)d * 2};
+    cuuint32_t box[2] = {(cuuint32_t)tc::KATOM, (cuuint32_t)tc::TILE};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = get_encode_fn()(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box,
+                                 estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                 CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    DFX_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
+}
+
+bool dfx_tc_supported(int d) { return d == 64 || d == 128; }
+
+// (re)build the bf16 planes of the centroids; call after training / import
+void dfx_tc_prepare_centroids(dfx_index* idx, cudaStream_t st) {
+    const int d = idx->cfg.d;
+    if (!dfx_tc_supported(d)) return;
+    const int64_t nlist = idx->cfg.nlist;
+    const int64_t nl_pad = dfx_ceil_div(nlist, tc::TILE) * tc::TILE;
+    idx->tc_cent.reserve((size_t)2 * nl_pad * d * 2);
+    DFX_LAUNCH(split_bf16_kernel, (unsigned)dfx_ceil_div(nl_pad * d, 256), 256, 0, st, idx->centroids.as<float>(),
+               nlist, nl_pad, d, idx->tc_cent.as<__nv_bfloat16>());
+    idx->tc_ready = true;
+}
+
+// screening pass: gmin[nq][ng] for a batch of rows against any centroid table with bf16 planes
+static void tc_screen(dfx_index* idx, int d, const float* d_x, int64_t nq, const void* cent_planes,
+                      const float* cnorm, int64_t nlist, int metric, float* gmin, cudaStream_t st) {
+    using namespace tc;
+    const int64_t nl_pad = dfx_ceil_div(nlist, TILE) * TILE;
+    const int64_t nq_pad = dfx_ceil_div(nq, TILE) * TILE;
+    const int ng = (int)(nl_pad / 32);
+    idx->tc_q.reserve((size_t)2 * nq_pad * d * 2);
+    DFX_LAUNCH(split_bf16_kernel, (unsigned)dfx_ceil_div(nq_pad * d, 256), 256, 0, st, d_x, nq, nq_pad, d,
+               idx->tc_q.as<__nv_bfloat16>());
+    CUtensorMap tmQ, tmC;
+    make_tmap(&tmQ, idx->tc_q.p, 2 * nq_pad, d);
+    make_tmap(&tmC, cent_planes, 2 * nl_pad, d);
+    const int qtiles = (int)(nq_pad / TILE), ctiles = (int)(nl_pad / TILE);
+    // enough CTAs to fill the machine a few times over, each walking a contiguous range of
+    // centroid tiles with its query tile resident
+    int csplit = (int)dfx_ceil_div(4 * 148, qtiles);
+    if (csplit > ctiles) csplit = ctiles;
+    if (csplit < 1) csplit = 1;
+    const int per = (int)dfx_ceil_div(ctiles, csplit);
+    csplit = (int)dfx_ceil_div(ctiles, per);
+    const int katoms = d / KATOM;
+    const size_t smem = (size_t)Smem::total(katoms) + 1024;
+    dim3 grid((unsigned)csplit, (unsigned)qtiles);
+    DFX_REQUIRE(qtiles <= 65535, "too many query tiles in one screening launch");
+    if (katoms == 2) {
+        auto kern = tc_coarse_kernel<2>;
+        DFX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        DFX_LAUNCH(kern, grid, THREADS, smem, st, tmQ, tmC, (int)nq, (int)nq_pad, (int)nlist, (int)nl_pad, cnorm,
+                   metric, per, gmin, ng);
+    } else {
+        auto kern = tc_coarse_kernel<1>;
+        DFX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        DFX_LAUNCH(kern, grid, THREADS, smem, st, tmQ, tmC, (int)nq, (int)nq_pad, (int)nlist, (int)nl_pad, cnorm,
+                   metric, per, gmin, ng);
+    }
+}
+
+// top-nprobe lists per query -> keys int32 [nq, nprobe] (exactly the oracle's coarse result)
+void dfx_tc_coarse_search(dfx_index* idx, const float* d_x, int64_t nq, int nprobe, int32_t* keys, cudaStream_t st) {
+    const int d = idx->cfg.d;
+    const int64_t nlist = idx->cfg.nlist;
+    const int64_t nl_pad = dfx_ceil_div(nlist, tc::TILE) * tc::TILE;
+    const int ng = (int)(nl_pad / 32);
+    int G = nprobe + 8;
+    if (G > ng) G = ng;
+    const int64_t QC = std::max<int64_t>(tc::TILE, ((64ll << 20) / ((int64_t)ng * 4)) / tc::TILE * tc::TILE);
+    idx->tc_gmin.reserve((size_t)std::min<int64_t>(nq, QC) * ng * 4);
+    idx->tc_groups.reserve((size_t)std::min<int64_t>(nq, QC) * G * 4);
+    idx->tc_cand.reserve((size_t)std::min<int64_t>(nq, QC) * G * 32 * 8);
+    for (int64_t q0 = 0; q0 < nq; q0 += QC) {
+        const int64_t qc = std::min(QC, nq - q0);
+        tc_screen(idx, d, d_x + q0 * d, qc, idx->tc_cent.p, idx->cnorm.as<float>(), nlist, idx->cfg.metric,
+                  idx->tc_gmin.as<float>(), st);
+        dfx_launch_select_cols(idx->tc_gmin.as<float>(), qc, ng, ng, G, 0, idx->tc_groups.as<int32_t>(), nullptr,
+                               nullptr, 0, st);
+        auto kern = rerank_kernel<false>;
+        DFX_LAUNCH(kern, (unsigned)qc, 128, (size_t)d * 4, st, d_x + q0 * d, d, idx->centroids.as<float>(),
+                   idx->cnorm.as<float>(), nlist, idx->cfg.metric, idx->tc_groups.as<int32_t>(), G,
+                   idx->tc_cand.as<uint64_t>(), (int32_t*)nullptr);
+        dfx_launch_select_comp(idx->tc_cand.as<uint64_t>(), qc, G * 32, (int64_t)G * 32, nprobe, keys + q0 * nprobe,
+                               st);
+    }
+}
+
+// nearest centroid per row (build path): same screening, 4 candidate groups, fused arg-min
+void dfx_tc_assign(dfx_index* idx, int d, const float* d_cent, const float* d_cnorm, int64_t nlist, int metric,
+                   int64_t n, const float* d_x, int32_t* d_assign, cudaStream_t st) {
+    const int64_t nl_pad = dfx_ceil_div(nlist, tc::TILE) * tc::TILE;
+    const int ng = (int)(nl_pad / 32);
+    constexpr int G = 4;
+    const int64_t RC = std::max<int64_t>(tc::TILE, ((256ll << 20) / ((int64_t)ng * 4)) / tc::TILE * tc::TILE);
+    idx->tc_gmin.reserve((size_t)std::min<int64_t>(n, RC) * ng * 4);
+    idx->tc_groups.reserve((size_t)std::min<int64_t>(n, RC) * G * 4);
+    // bf16 planes of this centroid table (k-means changes it every iteration; splitting is cheap)
+    idx->tc_cent_tmp.reserve((size_t)2 * nl_pad * d * 2);
+    DFX_LAUNCH(split_bf16_kernel, (unsigned)dfx_ceil_div(nl_pad * d, 256), 256, 0, st, d_cent, nlist, nl_pad, d,
+               idx->tc_cent_tmp.as<__nv_bfloat16>());
+    const void* cent_planes = idx->tc_cent_tmp.p;
+    for (int64_t r0 = 0; r0 < n; r0 += RC) {
+        const int64_t rc = std::min(RC, n - r0);
+        tc_screen(idx, d, d_x + r0 * d, rc, cent_planes, d_cnorm, nlist, metric, idx->tc_gmin.as<float>(), st);
+        auto topg = topg_small_kernel<G>;
+        DFX_LAUNCH(topg, (unsigned)dfx_ceil_div(rc, 8), 256, 0, st, idx->tc_gmin.as<float>(), rc, ng,
+                   idx->tc_groups.as<int32_t>());
+        auto kern = rerank_kernel<true>;
+        DFX_LAUNCH(kern, (unsigned)rc, 128, (size_t)d * 4, st, d_x + r0 * d, d, d_cent, d_cnorm, nlist, metric,
+                   idx->tc_groups.as<int32_t>(), G, (uint64_t*)nullptr, d_assign + r0);
+    }
+}

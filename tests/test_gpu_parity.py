@@ -314,3 +314,54 @@ def test_device_pointer_path_matches_host_path():
     _assert_same(D_t.cpu().numpy(), I_t.cpu().numpy(), Do, Io, "search_dev")
     assert stats["ndis"] == o.last_ndis
     _assert_same(*g.search(xq, 10), Do, Io, "host search after device search")
+
+
+# ------------------------------------------------------------------ K1 on tensor cores
+@pytest.mark.parametrize("kind,metric,d,M", [("ivf_pq", L2, 128, 32), ("ivf_flat", L2, 64, 0),
+                                             ("ivf_flat", IP, 128, 0), ("ivf_sq", L2, 128, 0)])
+def test_tensor_core_coarse_quantizer_matches_oracle(kind, metric, d, M):
+    """nlist >= 1024 and d in {64,128} route the coarse quantizer through tcgen05 (bf16 split
+    screening) + canonical fp32 re-rank: probe lists, hence results, must still be bit-identical
+    to the oracle's, and identical to the plain FFMA path."""
+    rs = np.random.RandomState(12)
+    nlist, n = 1024, 60_000
+    g, o, xb = _build_both(kind, metric, d, nlist, M, n, rs, via="gpu")
+    xq = np.concatenate([clustered(rs, 150, d, ncl=64), xb[:50] + 0.01 * rs.randn(50, d).astype(np.float32)])
+    for nprobe in (1, 7, 64):
+        g.nprobe = nprobe; o.nprobe = nprobe
+        Do, Io = o.search(xq, 10)
+        g.set_param("tensor_cores", 1)
+        Dg, Ig = g.search(xq, 10)
+        _assert_same(Dg, Ig, Do, Io, f"TC coarse {kind} nprobe={nprobe}")
+        assert g.last_stats()["ndis"] == o.last_ndis
+        g.set_param("tensor_cores", 0)
+        Df, If = g.search(xq, 10)
+        _assert_same(Df, If, Do, Io, f"FFMA coarse {kind} nprobe={nprobe}")
+    g.set_param("tensor_cores", 1)
+    D1, I1 = g.search(xq[3:4], 10)  # single query: a 128-row tile with one valid row
+    g.nprobe = 64
+    D1, I1 = g.search(xq[3:4], 10)
+    o.nprobe = 64
+    _assert_same(D1, I1, *o.search(xq[3:4], 10), "TC coarse nq=1")
+
+
+def test_tensor_core_assign_matches_oracle():
+    """add() with nlist >= 1024 assigns through the tensor-core screening + exact arg-min; the
+    lists must be those the oracle builds from the same trained state."""
+    from oracle import oracle as O
+
+    E = _engine()
+    rs = np.random.RandomState(13)
+    d, nlist, M, n = 128, 1024, 32, 80_000
+    xb = clustered(rs, n, d, ncl=700, sigma=0.5)
+    g = E.GpuIndex(E.KIND_IVF_PQ, d, L2, nlist=nlist, pq_m=M)
+    g.set_param("kmeans_niter", 6)
+    g.train(xb[:40000])
+    g.add(xb)
+    st = g.get_state()
+    o = O.OracleIVFPQ(d, nlist, M, 8, coarse_metric=L2)
+    o.centroids, o.codebooks, o.is_trained = st["centroids"], st["codebooks"], True
+    o.add(xb)
+    assert np.array_equal(o.list_off, st["list_off"])
+    assert np.array_equal(o.ids, st["ids"])
+    assert np.array_equal(o.codes, st["codes"])
