@@ -37,9 +37,12 @@ K = 10
 PQ_M = 32
 
 
+_T0 = time.time()
+
+
 def log(*a):
     if int(os.environ.get("RANK", "0")) == 0:
-        print("[bench]", *a, file=sys.stderr, flush=True)
+        print(f"[bench +{time.time() - _T0:7.1f}s]", *a, file=sys.stderr, flush=True)
 
 
 def nlist_for(n_shard: int) -> int:
@@ -257,6 +260,8 @@ def main():
 
     from distributed_faiss_b200 import engine, spmd
 
+    log("imports done")
+
     rank, local_rank, world = spmd.init_process_group_from_env()
     if args.impl == "reference" and rank != 0:
         return 0
@@ -339,6 +344,7 @@ def main():
             if recalls[cand] >= 0.95:
                 break
     _, I = run_search(xq[:n_eval].contiguous(), nprobe)
+    log(f"nprobe = {nprobe}")
     recall = recall_at_k(I, gt, gt_ok)
     r1 = float((I[:, :1] == gt[:, :1])[gt_ok].float().mean().item())
 
@@ -402,6 +408,7 @@ def main():
     ndis_step = float(np.mean([ndis_per_batch[it % len(batches)] for it in range(args.steps)]))
     launches_timed = launches * args.steps // (args.steps + args.warmup)
 
+    log(f"timed region done: {ms / args.steps:.3f} ms/step")
     # e2e: host buffers through the public call, H2D + D2H inside the timed region
     ms_e2e = timed(batches, args.steps, args.warmup, host=True)
     qps_e2e = args.steps * B / (ms_e2e / 1e3)
@@ -436,6 +443,7 @@ def main():
                 "launches_per_step": scan_launches / (args.steps + args.warmup),
                 "scan_share_of_step": scan_ms_per_step / (ms / args.steps) if ms else None}
 
+    log("e2e + sweep done")
     cb = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cb = cpu_baseline(shards[0], xq.cpu().numpy(), nprobe, args.cpu_queries, NSHARDS)
@@ -444,6 +452,7 @@ def main():
         Dg, Ig = shards[0].search(xq[:args.cpu_queries].cpu().numpy(), K)
         cb["gpu_equals_oracle"] = bool(np.array_equal(Dg, cb.pop("_D")) and np.array_equal(Ig, cb.pop("_I")))
 
+    log("cpu baseline done")
     if rank == 0:
         out = {
             "metric": "QPS at recall@10>=0.95, IVF-PQ d=128", "value": qps, "unit": "QPS", "n_gpus": world,

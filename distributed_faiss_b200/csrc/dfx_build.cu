@@ -75,7 +75,9 @@ __global__ void split_cluster_kernel(float* cent, int d, int empty, int big) {
     }
 }
 
-// PQ encode: grid (ceil(n/256), M); code_m = argmin_j l2_seq(r_m, P[m][j]), ties -> smaller j
+// PQ encode: grid (ceil(n/256), M); code_m = argmin_j l2_seq(r_m, P[m][j]), ties -> smaller j.
+// The residual sub-vector lives in registers (DS = dsub when it is one of the common sizes).
+template <int DS>
 __global__ void __launch_bounds__(256)
 pq_encode_kernel(const float* __restrict__ x, const float* __restrict__ cent,
                  const int32_t* __restrict__ assign, int64_t n, int d, int M, int ksub, int dsub,
@@ -91,15 +93,33 @@ pq_encode_kernel(const float* __restrict__ x, const float* __restrict__ cent,
     const float* c = cent + (size_t)assign[i] * d + m * dsub;
     float best = FLT_MAX;
     int bj = 0;
-    for (int j = 0; j < ksub; j++) {
-        float acc = 0.f;
-        for (int t = 0; t < dsub; t++) {
-            float df = (xi[t] - c[t]) - s_cb[j * dsub + t];
-            acc = __fmaf_rn(df, df, acc);
+    if (DS > 0) {
+        float r[DS > 0 ? DS : 1];
+#pragma unroll
+        for (int t = 0; t < DS; t++) r[t] = xi[t] - c[t];
+        for (int j = 0; j < ksub; j++) {
+            float acc = 0.f;
+#pragma unroll
+            for (int t = 0; t < DS; t++) {
+                float df = r[t] - s_cb[j * DS + t];
+                acc = __fmaf_rn(df, df, acc);
+            }
+            if (acc < best) {
+                best = acc;
+                bj = j;
+            }
         }
-        if (acc < best) {
-            best = acc;
-            bj = j;
+    } else {
+        for (int j = 0; j < ksub; j++) {
+            float acc = 0.f;
+            for (int t = 0; t < dsub; t++) {
+                float df = (xi[t] - c[t]) - s_cb[j * dsub + t];
+                acc = __fmaf_rn(df, df, acc);
+            }
+            if (acc < best) {
+                best = acc;
+                bj = j;
+            }
         }
     }
     codes[i * M + m] = (uint8_t)bj;
@@ -390,9 +410,18 @@ void dfx_add_impl(dfx_index* idx, int64_t n, const float* d_x, cudaStream_t st) 
     } else if (kind == DFX_IVF_PQ) {
         const int M = idx->M, ksub = idx->ksub, dsub = idx->dsub;
         dim3 grid(blocks_for(n, 256), (unsigned)M);
-        DFX_LAUNCH(pq_encode_kernel, grid, 256, (size_t)ksub * dsub * 4, st, d_x,
-                   idx->centroids.as<float>(), plist, n, d, M, ksub, dsub, idx->codebooks.as<float>(),
-                   (uint8_t*)prow);
+#define DFX_PQ_ENCODE(DS)                                                                       \
+    do {                                                                                        \
+        auto kern = pq_encode_kernel<DS>;                                                       \
+        DFX_LAUNCH(kern, grid, 256, (size_t)ksub * dsub * 4, st, d_x, idx->centroids.as<float>(), \
+                   plist, n, d, M, ksub, dsub, idx->codebooks.as<float>(), (uint8_t*)prow);     \
+    } while (0)
+        if (dsub == 2) DFX_PQ_ENCODE(2);
+        else if (dsub == 4) DFX_PQ_ENCODE(4);
+        else if (dsub == 8) DFX_PQ_ENCODE(8);
+        else if (dsub == 16) DFX_PQ_ENCODE(16);
+        else DFX_PQ_ENCODE(0);
+#undef DFX_PQ_ENCODE
         DFX_LAUNCH(pq_tvals_kernel, blocks_for(n, 128), 128, 0, st, (const uint8_t*)prow, plist,
                    (const int64_t*)nullptr, nlist, n, d, M, ksub, dsub, idx->codebooks.as<float>(),
                    idx->centroids.as<float>(), idx->p_tvals.as<float>() + idx->n_pending);

@@ -36,7 +36,8 @@ struct dfx_index {
     uint64_t train_seed = 1234;       // faiss Clustering default seed
 
     // tensor-core coarse quantizer (dfx_tc.cu): bf16 hi/lo planes and screening workspace
-    DevBuf tc_cent, tc_cent_tmp, tc_q, tc_gmin, tc_groups, tc_cand;
+    DevBuf tc_cent, tc_cent_tmp, tc_q, tc_gmin, tc_gmin2, tc_gargc, tc_groups, tc_cand, tc_qn, tc_amb;
+    float tc_cmax2 = 0.f;
     bool tc_ready = false;
     bool tc_enabled = true;
 

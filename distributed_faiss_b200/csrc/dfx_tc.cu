@@ -138,7 +138,7 @@ template <int KATOMS>
 __global__ void __launch_bounds__(tc::THREADS, 1)
 tc_coarse_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmC, int nq,
                  int nq_pad, int nlist, int nl_pad, const float* __restrict__ cnorm, int metric, int ctiles_per_cta,
-                 float* __restrict__ gmin, int ng) {
+                 float* __restrict__ gmin, float* __restrict__ gmin2, uint8_t* __restrict__ gargc, int ng) {
     using namespace tc;
     extern __shared__ unsigned char smem_raw_tc[];
     unsigned char* smem = reinterpret_cast<unsigned char*>(
@@ -262,27 +262,36 @@ tc_coarse_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             asm volatile("bar.sync 1, 128;" ::: "memory");
             mbar_wait(&t_full[buf], (t >> 1) & 1);
             tc_fence_after();
-            float gm[4];
+            float gm[4], gm2[4];
+            uint32_t ga = 0;
 #pragma unroll
             for (int ch = 0; ch < 4; ch++) {
                 uint32_t r[32];
                 tc_ld32(tmem_base + buf * TILE + ch * 32 + ((uint32_t)(quad * 32) << 16), r);
-                float m = __int_as_float(0x7f800000);
+                float m1 = __int_as_float(0x7f800000), m2 = m1;
+                uint32_t a1 = 0;
 #pragma unroll
                 for (int j = 0; j < 32; j++) {
                     const float ip = __uint_as_float(r[j]);
                     const float cn = s_cn[buf * TILE + ch * 32 + j];
                     const float v = (metric == DFX_METRIC_IP) ? (cn - ip) : fmaf(-2.f, ip, cn);
-                    m = fminf(m, v);
+                    const bool lt = v < m1;
+                    m2 = lt ? m1 : fminf(m2, v);
+                    a1 = lt ? (uint32_t)j : a1;
+                    m1 = lt ? v : m1;
                 }
-                gm[ch] = m;
+                gm[ch] = m1;
+                gm2[ch] = m2;
+                ga |= a1 << (8 * ch);
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&t_empty[buf]);
             if (grow < nq) {
-                float4 o = make_float4(gm[0], gm[1], gm[2], gm[3]);
-                *reinterpret_cast<float4*>(gmin + grow * ng + (col0 >> 5)) = o;
+                const int64_t o = grow * ng + (col0 >> 5);
+                *reinterpret_cast<float4*>(gmin + o) = make_float4(gm[0], gm[1], gm[2], gm[3]);
+                *reinterpret_cast<float4*>(gmin2 + o) = make_float4(gm2[0], gm2[1], gm2[2], gm2[3]);
+                *reinterpret_cast<uint32_t*>(gargc + o) = ga;
             }
         }
     }
@@ -338,53 +347,114 @@ __global__ void topg_small_kernel(const float* __restrict__ gmin, int64_t nq, in
     }
 }
 
-// exact canonical fp32 values of the candidate centroids: out[row][c] = comp(value, centroid)
-// ARGMIN: instead write the arg-min centroid of the row to assign[row]
+// Which columns of the selected groups can still matter?  With t = value of the nprobe-th
+// smallest group minimum and tol >= twice the screening error, every true top-nprobe centroid c
+// has approx(c) <= t + tol; inside its group it is either the arg-min column or has
+// approx(c) >= gmin2(group).  So a group is expanded to all 32 columns only if
+// gmin2 <= t + tol, otherwise its arg-min column is the only candidate.
+__device__ __forceinline__ float screen_tol(float qn2, float cmax2) {
+    return 1e-4f * sqrtf(qn2 * cmax2) + 1e-30f;
+}
+
+// exact canonical fp32 values of the candidates: out[row][c] = comp(value, centroid) (NONE for
+// unused slots).  ARGMIN: write the arg-min centroid to assign[row] instead.
+// rows: optional indirection (the CTA for list entry b handles row rows[b]); nrows_dev: its length.
 template <bool ARGMIN>
 __global__ void __launch_bounds__(128)
 rerank_kernel(const float* __restrict__ Q, int d, const float* __restrict__ cent, const float* __restrict__ cnorm,
-              int64_t nlist, int metric, const int32_t* __restrict__ groups, int G, uint64_t* __restrict__ out,
-              int32_t* __restrict__ assign) {
+              int64_t nlist, int metric, const int32_t* __restrict__ groups, int G, int nprobe,
+              const float* __restrict__ gmin, const float* __restrict__ gmin2, const uint8_t* __restrict__ gargc,
+              int ng, float cmax2, uint64_t* __restrict__ out, int32_t* __restrict__ assign,
+              const int32_t* __restrict__ rows, const int32_t* __restrict__ nrows_dev, int64_t nrows) {
     extern __shared__ float s_q[];
     __shared__ unsigned long long s_best[4];
-    const int64_t row = blockIdx.x;
-    for (int i = threadIdx.x; i < d; i += 128) s_q[i] = Q[row * d + i];
-    __syncthreads();
-    unsigned long long best = DFX_COMP_NONE;
+    __shared__ float s_thr;
     const int ncand = G * 32;
-    for (int c = threadIdx.x; c < ncand; c += 128) {
-        const int gid = groups[row * G + (c >> 5)];
-        const int64_t col = (int64_t)gid * 32 + (c & 31);
-        unsigned long long comp = DFX_COMP_NONE;
-        if (gid >= 0 && col < nlist) {
-            const float* x = cent + col * d;
-            float acc = 0.f;
-            for (int k = 0; k < d; k += 4) {
-                const float4 xv = *reinterpret_cast<const float4*>(x + k);
-                acc = __fmaf_rn(s_q[k + 0], xv.x, acc);
-                acc = __fmaf_rn(s_q[k + 1], xv.y, acc);
-                acc = __fmaf_rn(s_q[k + 2], xv.z, acc);
-                acc = __fmaf_rn(s_q[k + 3], xv.w, acc);
-            }
-            const float v = (metric == DFX_METRIC_IP) ? -acc : __fmaf_rn(-2.f, acc, cnorm[col]);
-            comp = dfx_comp(v, (uint32_t)col);
-        }
-        if (ARGMIN) best = comp < best ? comp : best;
-        else out[row * ncand + c] = comp;
-    }
-    if (ARGMIN) {
-#pragma unroll
-        for (int off = 16; off >= 1; off >>= 1) {
-            unsigned long long o = __shfl_xor_sync(0xffffffffu, best, off);
-            best = o < best ? o : best;
-        }
-        if ((threadIdx.x & 31) == 0) s_best[threadIdx.x >> 5] = best;
+    const int64_t limit = nrows_dev ? (int64_t)*nrows_dev : nrows;
+    for (int64_t b = blockIdx.x; b < limit; b += gridDim.x) {
+        const int64_t row = rows ? rows[b] : b;
+        __syncthreads();
+        for (int i = threadIdx.x; i < d; i += 128) s_q[i] = Q[row * d + i];
         __syncthreads();
         if (threadIdx.x == 0) {
-            for (int w = 1; w < 4; w++) best = s_best[w] < best ? s_best[w] : best;
-            assign[row] = (best == DFX_COMP_NONE) ? -1 : (int32_t)(uint32_t)best;
+            float qn2 = 0.f;
+            for (int i = 0; i < d; i++) qn2 += s_q[i] * s_q[i];
+            // the bound needs nprobe distinct groups: with fewer groups than probes nothing is pruned
+            const int gk = (nprobe <= G) ? groups[row * G + nprobe - 1] : -1;
+            s_thr = (gk >= 0 ? gmin[row * ng + gk] : __int_as_float(0x7f800000)) + screen_tol(qn2, cmax2);
+        }
+        __syncthreads();
+        const float thr = s_thr;
+        unsigned long long best = DFX_COMP_NONE;
+        for (int c = threadIdx.x; c < ncand; c += 128) {
+            const int gid = groups[row * G + (c >> 5)];
+            unsigned long long comp = DFX_COMP_NONE;
+            if (gid >= 0) {
+                const int64_t o = row * ng + gid;
+                const bool expand = gmin2[o] <= thr;
+                const bool live = gmin[o] <= thr && (expand || (c & 31) == (int)gargc[o]);
+                const int64_t col = (int64_t)gid * 32 + (c & 31);
+                if (live && col < nlist) {
+                    const float* x = cent + col * d;
+                    float acc = 0.f;
+                    for (int k = 0; k < d; k += 4) {
+                        const float4 xv = *reinterpret_cast<const float4*>(x + k);
+                        acc = __fmaf_rn(s_q[k + 0], xv.x, acc);
+                        acc = __fmaf_rn(s_q[k + 1], xv.y, acc);
+                        acc = __fmaf_rn(s_q[k + 2], xv.z, acc);
+                        acc = __fmaf_rn(s_q[k + 3], xv.w, acc);
+                    }
+                    const float v = (metric == DFX_METRIC_IP) ? -acc : __fmaf_rn(-2.f, acc, cnorm[col]);
+                    comp = dfx_comp(v, (uint32_t)col);
+                }
+            }
+            if (ARGMIN) best = comp < best ? comp : best;
+            else out[row * ncand + c] = comp;
+        }
+        if (ARGMIN) {
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) {
+                unsigned long long o = __shfl_xor_sync(0xffffffffu, best, off);
+                best = o < best ? o : best;
+            }
+            if ((threadIdx.x & 31) == 0) s_best[threadIdx.x >> 5] = best;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                for (int w = 1; w < 4; w++) best = s_best[w] < best ? s_best[w] : best;
+                assign[row] = (best == DFX_COMP_NONE) ? -1 : (int32_t)(uint32_t)best;
+            }
         }
     }
+}
+
+// assign fast path: one thread per row decides from the screening summary alone when the best
+// group's arg-min column is unambiguous (no other column within tol); other rows are queued
+// for the exact evaluation above.
+__global__ void assign_resolve_kernel(const float* __restrict__ qnorm2, const int32_t* __restrict__ groups,
+                                      const float* __restrict__ gmin, const float* __restrict__ gmin2,
+                                      const uint8_t* __restrict__ gargc, int ng, float cmax2, int64_t n,
+                                      int32_t* __restrict__ assign, int32_t* __restrict__ amb_rows,
+                                      int32_t* __restrict__ amb_count) {
+    const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= n) return;
+    const int g0 = groups[row * 2 + 0], g1 = groups[row * 2 + 1];
+    const int64_t o0 = row * ng + g0;
+    const float thr = gmin[o0] + screen_tol(qnorm2[row], cmax2);
+    const bool clear = gmin2[o0] > thr && (g1 < 0 || gmin[row * ng + g1] > thr);
+    if (clear) {
+        assign[row] = g0 * 32 + (int)gargc[o0];
+    } else {
+        assign[row] = -1;
+        amb_rows[atomicAdd(amb_count, 1)] = (int32_t)row;
+    }
+}
+
+__global__ void max_reduce_kernel(const float* __restrict__ x, int64_t n, float* __restrict__ out) {
+    float m = 0.f;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        m = fmaxf(m, x[i]);
+    for (int off = 16; off >= 1; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+    if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<int*>(out), __float_as_int(m));  // m >= 0
 }
 
 // ------------------------------------------------------------------ host side
@@ -418,6 +488,17 @@ static void make_tmap(CUtensorMap* tm, const void* base, int64_t rows, int d) {
 
 bool dfx_tc_supported(int d) { return d == 64 || d == 128; }
 
+// max |c|^2 of a centroid table (for the screening tolerance), synchronises
+static float max_norm2(dfx_index* idx, const float* cnorm, int64_t nlist, cudaStream_t st) {
+    idx->w_misc.reserve(8);
+    DFX_CUDA(cudaMemsetAsync(idx->w_misc.p, 0, 4, st));
+    DFX_LAUNCH(max_reduce_kernel, 64, 256, 0, st, cnorm, nlist, idx->w_misc.as<float>());
+    float h = 0.f;
+    DFX_CUDA(cudaMemcpyAsync(&h, idx->w_misc.p, 4, cudaMemcpyDeviceToHost, st));
+    DFX_CUDA(cudaStreamSynchronize(st));
+    return h;
+}
+
 // (re)build the bf16 planes of the centroids; call after training / import
 void dfx_tc_prepare_centroids(dfx_index* idx, cudaStream_t st) {
     const int d = idx->cfg.d;
@@ -427,12 +508,14 @@ void dfx_tc_prepare_centroids(dfx_index* idx, cudaStream_t st) {
     idx->tc_cent.reserve((size_t)2 * nl_pad * d * 2);
     DFX_LAUNCH(split_bf16_kernel, (unsigned)dfx_ceil_div(nl_pad * d, 256), 256, 0, st, idx->centroids.as<float>(),
                nlist, nl_pad, d, idx->tc_cent.as<__nv_bfloat16>());
+    idx->tc_cmax2 = max_norm2(idx, idx->cnorm.as<float>(), nlist, st);
     idx->tc_ready = true;
 }
 
 // screening pass: gmin[nq][ng] for a batch of rows against any centroid table with bf16 planes
 static void tc_screen(dfx_index* idx, int d, const float* d_x, int64_t nq, const void* cent_planes,
-                      const float* cnorm, int64_t nlist, int metric, float* gmin, cudaStream_t st) {
+                      const float* cnorm, int64_t nlist, int metric, float* gmin, float* gmin2, uint8_t* gargc,
+                      cudaStream_t st) {
     using namespace tc;
     const int64_t nl_pad = dfx_ceil_div(nlist, TILE) * TILE;
     const int64_t nq_pad = dfx_ceil_div(nq, TILE) * TILE;
@@ -459,12 +542,12 @@ static void tc_screen(dfx_index* idx, int d, const float* d_x, int64_t nq, const
         auto kern = tc_coarse_kernel<2>;
         DFX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         DFX_LAUNCH(kern, grid, THREADS, smem, st, tmQ, tmC, (int)nq, (int)nq_pad, (int)nlist, (int)nl_pad, cnorm,
-                   metric, per, gmin, ng);
+                   metric, per, gmin, gmin2, gargc, ng);
     } else {
         auto kern = tc_coarse_kernel<1>;
         DFX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         DFX_LAUNCH(kern, grid, THREADS, smem, st, tmQ, tmC, (int)nq, (int)nq_pad, (int)nlist, (int)nl_pad, cnorm,
-                   metric, per, gmin, ng);
+                   metric, per, gmin, gmin2, gargc, ng);
     }
 }
 
@@ -477,46 +560,70 @@ void dfx_tc_coarse_search(dfx_index* idx, const float* d_x, int64_t nq, int npro
     int G = nprobe + 8;
     if (G > ng) G = ng;
     const int64_t QC = std::max<int64_t>(tc::TILE, ((64ll << 20) / ((int64_t)ng * 4)) / tc::TILE * tc::TILE);
-    idx->tc_gmin.reserve((size_t)std::min<int64_t>(nq, QC) * ng * 4);
-    idx->tc_groups.reserve((size_t)std::min<int64_t>(nq, QC) * G * 4);
-    idx->tc_cand.reserve((size_t)std::min<int64_t>(nq, QC) * G * 32 * 8);
+    const int64_t qmax = std::min<int64_t>(nq, QC);
+    idx->tc_gmin.reserve((size_t)qmax * ng * 4);
+    idx->tc_gmin2.reserve((size_t)qmax * ng * 4);
+    idx->tc_gargc.reserve((size_t)qmax * ng);
+    idx->tc_groups.reserve((size_t)qmax * G * 4);
+    idx->tc_cand.reserve((size_t)qmax * G * 32 * 8);
     for (int64_t q0 = 0; q0 < nq; q0 += QC) {
         const int64_t qc = std::min(QC, nq - q0);
         tc_screen(idx, d, d_x + q0 * d, qc, idx->tc_cent.p, idx->cnorm.as<float>(), nlist, idx->cfg.metric,
-                  idx->tc_gmin.as<float>(), st);
+                  idx->tc_gmin.as<float>(), idx->tc_gmin2.as<float>(), idx->tc_gargc.as<uint8_t>(), st);
         dfx_launch_select_cols(idx->tc_gmin.as<float>(), qc, ng, ng, G, 0, idx->tc_groups.as<int32_t>(), nullptr,
                                nullptr, 0, st);
         auto kern = rerank_kernel<false>;
         DFX_LAUNCH(kern, (unsigned)qc, 128, (size_t)d * 4, st, d_x + q0 * d, d, idx->centroids.as<float>(),
-                   idx->cnorm.as<float>(), nlist, idx->cfg.metric, idx->tc_groups.as<int32_t>(), G,
-                   idx->tc_cand.as<uint64_t>(), (int32_t*)nullptr);
+                   idx->cnorm.as<float>(), nlist, idx->cfg.metric, idx->tc_groups.as<int32_t>(), G, nprobe,
+                   idx->tc_gmin.as<float>(), idx->tc_gmin2.as<float>(), idx->tc_gargc.as<uint8_t>(), ng,
+                   idx->tc_cmax2, idx->tc_cand.as<uint64_t>(), (int32_t*)nullptr, (const int32_t*)nullptr,
+                   (const int32_t*)nullptr, qc);
         dfx_launch_select_comp(idx->tc_cand.as<uint64_t>(), qc, G * 32, (int64_t)G * 32, nprobe, keys + q0 * nprobe,
                                st);
     }
 }
 
-// nearest centroid per row (build path): same screening, 4 candidate groups, fused arg-min
+// nearest centroid per row (build path): screening, then the answer straight from the screening
+// summary when it is unambiguous, exact canonical evaluation for the (rare) ambiguous rows
 void dfx_tc_assign(dfx_index* idx, int d, const float* d_cent, const float* d_cnorm, int64_t nlist, int metric,
                    int64_t n, const float* d_x, int32_t* d_assign, cudaStream_t st) {
     const int64_t nl_pad = dfx_ceil_div(nlist, tc::TILE) * tc::TILE;
     const int ng = (int)(nl_pad / 32);
-    constexpr int G = 4;
+    constexpr int G = 2;
     const int64_t RC = std::max<int64_t>(tc::TILE, ((256ll << 20) / ((int64_t)ng * 4)) / tc::TILE * tc::TILE);
-    idx->tc_gmin.reserve((size_t)std::min<int64_t>(n, RC) * ng * 4);
-    idx->tc_groups.reserve((size_t)std::min<int64_t>(n, RC) * G * 4);
+    const int64_t rmax = std::min<int64_t>(n, RC);
+    idx->tc_gmin.reserve((size_t)rmax * ng * 4);
+    idx->tc_gmin2.reserve((size_t)rmax * ng * 4);
+    idx->tc_gargc.reserve((size_t)rmax * ng);
+    idx->tc_groups.reserve((size_t)rmax * G * 4);
+    idx->tc_qn.reserve((size_t)rmax * 4);
+    idx->tc_amb.reserve((size_t)(rmax + 1) * 4);
     // bf16 planes of this centroid table (k-means changes it every iteration; splitting is cheap)
     idx->tc_cent_tmp.reserve((size_t)2 * nl_pad * d * 2);
     DFX_LAUNCH(split_bf16_kernel, (unsigned)dfx_ceil_div(nl_pad * d, 256), 256, 0, st, d_cent, nlist, nl_pad, d,
                idx->tc_cent_tmp.as<__nv_bfloat16>());
     const void* cent_planes = idx->tc_cent_tmp.p;
+    const float cmax2 = max_norm2(idx, d_cnorm, nlist, st);
     for (int64_t r0 = 0; r0 < n; r0 += RC) {
         const int64_t rc = std::min(RC, n - r0);
-        tc_screen(idx, d, d_x + r0 * d, rc, cent_planes, d_cnorm, nlist, metric, idx->tc_gmin.as<float>(), st);
+        const float* xr = d_x + r0 * d;
+        tc_screen(idx, d, xr, rc, cent_planes, d_cnorm, nlist, metric, idx->tc_gmin.as<float>(),
+                  idx->tc_gmin2.as<float>(), idx->tc_gargc.as<uint8_t>(), st);
         auto topg = topg_small_kernel<G>;
         DFX_LAUNCH(topg, (unsigned)dfx_ceil_div(rc, 8), 256, 0, st, idx->tc_gmin.as<float>(), rc, ng,
                    idx->tc_groups.as<int32_t>());
+        dfx_launch_row_norms(xr, rc, d, idx->tc_qn.as<float>(), st);
+        int32_t* amb_count = idx->tc_amb.as<int32_t>();
+        int32_t* amb_rows = amb_count + 1;
+        DFX_CUDA(cudaMemsetAsync(amb_count, 0, 4, st));
+        DFX_LAUNCH(assign_resolve_kernel, (unsigned)dfx_ceil_div(rc, 256), 256, 0, st, idx->tc_qn.as<float>(),
+                   idx->tc_groups.as<int32_t>(), idx->tc_gmin.as<float>(), idx->tc_gmin2.as<float>(),
+                   idx->tc_gargc.as<uint8_t>(), ng, cmax2, rc, d_assign + r0, amb_rows, amb_count);
         auto kern = rerank_kernel<true>;
-        DFX_LAUNCH(kern, (unsigned)rc, 128, (size_t)d * 4, st, d_x + r0 * d, d, d_cent, d_cnorm, nlist, metric,
-                   idx->tc_groups.as<int32_t>(), G, (uint64_t*)nullptr, d_assign + r0);
+        const unsigned grid = (unsigned)std::min<int64_t>(rc, 148 * 16);
+        DFX_LAUNCH(kern, grid, 128, (size_t)d * 4, st, xr, d, d_cent, d_cnorm, nlist, metric,
+                   idx->tc_groups.as<int32_t>(), G, 1, idx->tc_gmin.as<float>(), idx->tc_gmin2.as<float>(),
+                   idx->tc_gargc.as<uint8_t>(), ng, cmax2, (uint64_t*)nullptr, d_assign + r0,
+                   (const int32_t*)amb_rows, (const int32_t*)amb_count, rc);
     }
 }
