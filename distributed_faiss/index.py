@@ -1,0 +1,5 @@
+"""Alias of distributed_faiss_b200.index (drop-in import path, see distributed_faiss/__init__.py)."""
+from distributed_faiss_b200.index import *  # noqa: F401,F403
+from distributed_faiss_b200 import index as _impl
+
+globals().update({k: v for k, v in vars(_impl).items() if not k.startswith("__")})

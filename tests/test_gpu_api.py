@@ -1,0 +1,160 @@
+"""GPU tests at the API level: the reference's integration scenarios driven through
+IndexServer / IndexClient / ShardGroup with the CUDA engine (no test doubles)."""
+import os
+import socket
+import tempfile
+import threading
+import time
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def free_port():
+    with socket.socket() as s:
+        s.bind(("", 0))
+        return s.getsockname()[1]
+
+
+def make_client(ports):
+    from distributed_faiss_b200.client import IndexClient
+
+    with tempfile.NamedTemporaryFile("w", suffix=".txt", delete=False) as fh:
+        fh.write(f"{len(ports)}\n")
+        for p in ports:
+            fh.write(f"localhost,{p}\n")
+    try:
+        return IndexClient(fh.name)
+    finally:
+        os.unlink(fh.name)
+
+
+def wait_trained(client, index_id, timeout=120):
+    from distributed_faiss_b200.index_state import IndexState
+
+    t0 = time.time()
+    while client.get_state(index_id) != IndexState.TRAINED:
+        assert time.time() - t0 < timeout
+        time.sleep(0.05)
+
+
+@pytest.fixture(scope="module")
+def cluster():
+    from distributed_faiss_b200.server import IndexServer
+
+    dirs = [tempfile.TemporaryDirectory(), tempfile.TemporaryDirectory()]
+    ports = [free_port() for _ in range(4)]
+    servers = []
+    for rank, port in enumerate(ports):
+        s = IndexServer(rank, dirs[0].name)
+        threading.Thread(target=s.start_blocking, args=(port,), daemon=True).start()
+        servers.append(s)
+    sp = free_port()
+    single = IndexServer(0, dirs[1].name)
+    threading.Thread(target=single.start_blocking, args=(sp,), daemon=True).start()
+    time.sleep(0.3)
+    yield {"ports": ports, "single": sp, "dirs": dirs}
+    for s in servers + [single]:
+        s.stop()
+
+
+def test_result_aggregation_on_device():
+    """reference tests/test_integration.py:181-203 through IndexClient._aggregate_results -> K6"""
+    from distributed_faiss_b200.client import IndexClient
+
+    mock = [(np.array([[12.1, 13.2, 13.3, 14.3]], dtype=np.float32), [[1465, 1460, 443197, 1340]], None),
+            (np.array([[8.1, 12.6, 13.1, 17.4]], dtype=np.float32), [[0, 14, 3, 1]], None)]
+    D, i_min = IndexClient._aggregate_results(mock, 4, 1, False, False)
+    Dmax, i_max = IndexClient._aggregate_results(mock, 4, 1, True, False)
+    assert i_min == [[0, 1465, 14, 3]] and i_max == [[1, 1340, 443197, 1460]]
+    assert np.array_equal(D, np.array([[8.1, 12.1, 12.6, 13.1]], dtype=np.float32))
+    assert np.array_equal(Dmax, np.array([[-17.4, -14.3, -13.3, -13.2]], dtype=np.float32))
+
+
+def test_sharded_equals_unsharded_exactly(cluster):
+    """reference tests/test_integration.py:205-265 with the CUDA engine (flat, d=512, k=5)"""
+    from distributed_faiss_b200.index_cfg import IndexCfg
+
+    rs = np.random.RandomState(0)
+    d, index_id = 512, "g_same"
+    cfg = IndexCfg(index_builder_type="flat", dim=d)
+    single = make_client([cluster["single"]])
+    multi = make_client(cluster["ports"])
+    single.create_index(index_id, cfg)
+    multi.create_index(index_id, cfg)
+    for _ in range(10):
+        n = int(rs.randint(1, 3000))
+        emb = rs.rand(n, d).astype(np.float32)
+        meta = [f"m{rs.randint(1 << 30)}" for _ in range(n)]
+        multi.add_index_data(index_id, emb, meta, False)
+        single.add_index_data(index_id, emb, meta, False)
+    multi.sync_train(index_id)
+    single.sync_train(index_id)
+    wait_trained(multi, index_id)
+    wait_trained(single, index_id)
+    assert multi.get_ntotal(index_id) == single.get_ntotal(index_id)
+    q = rs.rand(16, d).astype(np.float32)
+    s_aggr, m_aggr = multi.search(q, 5, index_id)
+    s_single, m_single = single.search(q, 5, index_id)
+    assert (s_aggr == s_single).all() and m_aggr == m_single
+    multi.close(); single.close()
+
+
+def test_knnlm_pipeline_save_load(cluster):
+    """knnlm (IVF-PQ) through the API: train, add, set_nprobe, search, save, reload, same answers"""
+    from distributed_faiss_b200.index_cfg import IndexCfg
+
+    rs = np.random.RandomState(1)
+    d, index_id = 128, "g_knnlm"
+    cfg = IndexCfg(index_builder_type="knnlm", dim=d, centroids=32, metric="l2", train_num=3000, code_size=32)
+    client = make_client([cluster["single"]])
+    client.create_index(index_id, cfg)
+    centers = rs.randn(40, d).astype(np.float32)
+    for b in range(6):
+        x = (centers[rs.randint(0, 40, 1000)] + 0.2 * rs.randn(1000, d)).astype(np.float32)
+        client.add_index_data(index_id, x, list(range(b * 1000, (b + 1) * 1000)), False)
+    wait_trained(client, index_id)
+    assert client.get_ntotal(index_id) == 6000
+    client.set_nprobe(index_id, 8)                     # quirk B3: knnlm starts with nprobe 1
+    D, meta = client.search(x[:10], 5, index_id)
+    assert all(row[0] == 5000 + i for i, row in enumerate(meta))   # each query finds itself first
+    D2, meta2, embs = client.search(x[:10], 5, index_id, return_embeddings=True)
+    assert np.array_equal(D, D2) and np.asarray(embs).shape == (10, 5, d)
+    client.save_index(index_id)
+    client.close()
+    c2 = make_client([cluster["single"]])
+    assert c2.load_index(index_id, cfg)
+    c2.set_nprobe(index_id, 8)
+    D3, meta3 = c2.search(x[:10], 5, index_id)
+    assert np.array_equal(D, D3) and meta == meta3
+    c2.close()
+
+
+def test_shard_group_single_rank_matches_socket_client():
+    """the device data plane (ShardGroup, world 1, 4 shards on one GPU) returns what the socket
+    client returns for the same shards"""
+    import torch
+    from distributed_faiss_b200 import engine, spmd
+    from distributed_faiss_b200.client import IndexClient
+
+    rs = np.random.RandomState(2)
+    d, k = 64, 7
+    shards, tables, results, base = [], [], [], 0
+    xq = rs.rand(33, d).astype(np.float32)
+    for s in range(4):
+        x = rs.rand(700 + 50 * s, d).astype(np.float32)
+        ix = engine.GpuIndex(engine.KIND_FLAT, d, engine.METRIC_INNER_PRODUCT)
+        ix.add(x)
+        shards.append(ix)
+        tables.append(torch.arange(base, base + x.shape[0], dtype=torch.int64, device="cuda"))
+        D, I = ix.search(xq, k)
+        results.append((D, (I + base).tolist(), None))
+        base += x.shape[0]
+    group = spmd.ShardGroup(shards, tables)
+    D_dev, I_dev = group.search(torch.from_numpy(xq).cuda(), k, maximize=True)
+    D_ref, meta_ref = IndexClient._aggregate_results(results, k, xq.shape[0], True, False)
+    assert np.array_equal(D_dev.cpu().numpy(), D_ref) and I_dev.cpu().tolist() == meta_ref
+    Dh, Ih = group.search_host(xq, k, maximize=True)
+    assert np.array_equal(Dh, D_ref) and Ih.tolist() == meta_ref
