@@ -437,7 +437,7 @@ def main():
     bytes_per_launch /= launches_per_search
     achieved = bytes_per_launch / (per_launch_ms * 1e-3) / 1e9 if per_launch_ms > 0 else 0.0
     scan_ms_per_step = scan_ms / (args.steps + args.warmup)
-    roofline = {"kernel": "scan_pq_kernel<32>", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    roofline = {"kernel": "scan_pq_il_kernel (IVF-PQ list scan, interleaved M=32)", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                 "bytes_per_launch": bytes_per_launch, "ms_per_launch": per_launch_ms,
                 "launches_per_step": scan_launches / (args.steps + args.warmup),

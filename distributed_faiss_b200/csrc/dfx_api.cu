@@ -71,7 +71,7 @@ int dfx_create(const dfx_cfg* cfg, dfx_index** out) {
         DFX_REQUIRE(cfg->pq_nbits == 8, "IVF-PQ: only 8 bits per sub-quantizer are supported");
         DFX_REQUIRE(cfg->pq_m >= 4 && cfg->pq_m % 4 == 0 && cfg->d % cfg->pq_m == 0,
                     "IVF-PQ: the number of sub-quantizers must be a multiple of 4 that divides d");
-        DFX_REQUIRE((size_t)cfg->pq_m * 256 * 4 <= 160 * 1024, "IVF-PQ: M too large for shared memory");
+        DFX_REQUIRE(cfg->pq_m <= 64, "IVF-PQ: at most 64 sub-quantizers are supported");
         idx->M = cfg->pq_m;
         idx->ksub = 256;
         idx->dsub = cfg->d / cfg->pq_m;
@@ -105,6 +105,14 @@ int dfx_set_param(dfx_index* idx, const char* name, double value) {
     else if (n == "max_points_per_centroid") idx->max_points_per_centroid = (int)value;
     else if (n == "train_seed") idx->train_seed = (uint64_t)value;
     else if (n == "tensor_cores") idx->tc_enabled = value != 0;
+    else if (n == "interleaved") {
+        std::lock_guard<std::mutex> lk(idx->mu);
+        DeviceGuard g(idx->cfg.device);
+        idx->join_dev();
+        idx->il_enabled = value != 0;
+        if (!idx->il_enabled) dfx_pq_il_to_rm(idx, idx->stream);
+        else if (idx->trained && idx->n_pending == 0 && idx->n_sorted > 0) dfx_pq_rm_to_il(idx, idx->stream);
+    }
     else throw DfxError{"unknown parameter " + n};
     DFX_API_END
 }
@@ -326,6 +334,22 @@ int dfx_get_array(dfx_index* idx, const char* name, void* out, int64_t max_bytes
     idx->join_dev();
     if (idx->n_pending > 0) dfx_finalize_impl(idx, idx->stream);
     std::string n(name);
+    struct Restore {  // the exchange format is row-major; put the interleaved form back afterwards
+        dfx_index* i;
+        bool on;
+        ~Restore() {
+            if (on) {
+                try {
+                    dfx_pq_rm_to_il(i, i->stream);
+                } catch (...) {
+                }
+            }
+        }
+    } restore{idx, false};
+    if (idx->il && (n == "codes" || n == "tvals" || n == "ids")) {
+        dfx_pq_il_to_rm(idx, idx->stream);
+        restore.on = true;
+    }
     const int64_t nt = idx->n_sorted, nlist = idx->cfg.nlist, d = idx->cfg.d;
     const void* src = nullptr;
     int64_t bytes = 0;
@@ -358,6 +382,7 @@ int dfx_set_array(dfx_index* idx, const char* name, const void* in, int64_t nbyt
     DeviceGuard g(idx->cfg.device);
     idx->join_dev();
     std::string n(name);
+    if (idx->il) dfx_pq_il_to_rm(idx, idx->stream);  // imports arrive row-major
     const int64_t nlist = idx->cfg.nlist, d = idx->cfg.d;
     auto upload = [&](DevBuf& b, int64_t bytes) {
         b.reserve((size_t)std::max<int64_t>(bytes, 4));
@@ -421,6 +446,7 @@ int dfx_import_done(dfx_index* idx) {
         if (idx->cfg.kind == DFX_IVF_PQ) {
             DFX_REQUIRE(idx->codebooks.p, "import: codebooks are required");
             dfx_compute_tvals_sorted(idx, idx->stream);  // K7 recomputes the per-vector term
+            dfx_pq_rm_to_il(idx, idx->stream);
         }
         dfx_tc_prepare_centroids(idx, idx->stream);
         DFX_CUDA(cudaStreamSynchronize(idx->stream));

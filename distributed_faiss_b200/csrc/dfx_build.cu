@@ -445,6 +445,7 @@ void dfx_compute_tvals_sorted(dfx_index* idx, cudaStream_t st) {
 // ------------------------------------------------------------------ finalize: stage -> lists
 void dfx_finalize_impl(dfx_index* idx, cudaStream_t st) {
     if (!idx->is_ivf() || idx->n_pending == 0) return;
+    if (idx->il) dfx_pq_il_to_rm(idx, st);  // merge happens on the row-major form
     const int64_t na = idx->n_sorted, nb = idx->n_pending, n = na + nb;
     const int64_t nlist = idx->cfg.nlist;
     const size_t rb = idx->row_bytes();
@@ -516,19 +517,23 @@ void dfx_finalize_impl(dfx_index* idx, cudaStream_t st) {
     idx->n_sorted = n;
     idx->n_pending = 0;
     idx->inv_valid = false;
+    dfx_pq_rm_to_il(idx, st);  // IVF-PQ, M == 32: interleaved blocks for the scan (no-op otherwise)
 }
 
 // ------------------------------------------------------------------ reconstruct
 __global__ void invert_ids_kernel(const int32_t* __restrict__ ids, int64_t n, int32_t* __restrict__ inv) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) inv[ids[i]] = (int32_t)i;
+    if (i < n && ids[i] >= 0) inv[ids[i]] = (int32_t)i;
 }
 
+// il != 0 (IVF-PQ interleaved): `inv` holds padded block positions and codes are read from
+// the interleaved blocks (byte [m*32 + (v ^ m)] of block pos/32, v = pos%32)
 __global__ void reconstruct_kernel(int kind, int d, int M, int ksub, int dsub, int64_t ntotal,
                                    int64_t nlist, const int64_t* __restrict__ want,
                                    const int32_t* __restrict__ inv, const void* __restrict__ rows,
                                    const int64_t* __restrict__ list_off, const float* __restrict__ cent,
-                                   const float* __restrict__ codebooks, float* __restrict__ out) {
+                                   const float* __restrict__ codebooks, int il,
+                                   const int64_t* __restrict__ blk_off, float* __restrict__ out) {
     const int64_t r = blockIdx.x;
     const int64_t id = want[r];
     if (id < 0 || id >= ntotal) {
@@ -538,10 +543,12 @@ __global__ void reconstruct_kernel(int kind, int d, int M, int ksub, int dsub, i
     const int64_t pos = (kind == DFX_FLAT) ? id : inv[id];
     int64_t l = 0;
     if (kind == DFX_IVF_PQ || kind == DFX_IVF_SQ16) {
+        const int64_t* off = il ? blk_off : list_off;
+        const int64_t key = il ? (pos >> 5) : pos;
         int64_t lo = 0, hi = nlist;
         while (hi - lo > 1) {
             int64_t mid = (lo + hi) >> 1;
-            if (list_off[mid] <= pos) lo = mid; else hi = mid;
+            if (off[mid] <= key) lo = mid; else hi = mid;
         }
         l = lo;
     }
@@ -553,7 +560,9 @@ __global__ void reconstruct_kernel(int kind, int d, int M, int ksub, int dsub, i
             v = cent[(size_t)l * d + k] + __half2float(reinterpret_cast<const __half*>(rows)[pos * d + k]);
         } else {
             int m = k / dsub;
-            int code = reinterpret_cast<const uint8_t*>(rows)[pos * M + m];
+            int code;
+            if (il) code = reinterpret_cast<const uint8_t*>(rows)[(pos >> 5) * 1024 + m * 32 + ((int)(pos & 31) ^ m)];
+            else code = reinterpret_cast<const uint8_t*>(rows)[pos * M + m];
             v = cent[(size_t)l * d + k] + codebooks[((size_t)m * ksub + code) * dsub + (k - m * dsub)];
         }
         out[r * d + k] = v;
@@ -565,14 +574,17 @@ void dfx_reconstruct_impl(dfx_index* idx, int64_t n, const int64_t* d_ids, float
     if (n <= 0) return;
     if (idx->n_pending > 0) dfx_finalize_impl(idx, st);
     const int64_t nt = idx->n_sorted;
+    const int il = idx->il ? 1 : 0;
     if (idx->is_ivf() && !idx->inv_valid) {
         idx->inv.reserve((size_t)std::max<int64_t>(nt, 1) * 4);
-        if (nt > 0)
-            DFX_LAUNCH(invert_ids_kernel, blocks_for(nt, 256), 256, 0, st, idx->ids.as<int32_t>(), nt,
-                       idx->inv.as<int32_t>());
+        const int64_t npos = il ? idx->nblk * 32 : nt;
+        if (npos > 0)
+            DFX_LAUNCH(invert_ids_kernel, blocks_for(npos, 256), 256, 0, st,
+                       il ? idx->il_ids.as<int32_t>() : idx->ids.as<int32_t>(), npos, idx->inv.as<int32_t>());
         idx->inv_valid = true;
     }
     DFX_LAUNCH(reconstruct_kernel, (unsigned)n, 128, 0, st, idx->cfg.kind, idx->cfg.d, idx->M, idx->ksub,
-               idx->dsub, nt, idx->cfg.nlist, d_ids, idx->inv.as<int32_t>(), idx->payload.p,
-               idx->list_off.as<int64_t>(), idx->centroids.as<float>(), idx->codebooks.as<float>(), d_out);
+               idx->dsub, nt, idx->cfg.nlist, d_ids, idx->inv.as<int32_t>(),
+               il ? (const void*)idx->il_codes.p : (const void*)idx->payload.p, idx->list_off.as<int64_t>(),
+               idx->centroids.as<float>(), idx->codebooks.as<float>(), il, idx->blk_off.as<int64_t>(), d_out);
 }

@@ -32,17 +32,40 @@ struct DfxError {
     } while (0)
 
 // every kernel launch goes through this so that dfx_launch_count() is honest
-#define DFX_LAUNCH(kernel, grid, block, smem, stream, ...)                  \
-    do {                                                                    \
-        kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);         \
-        g_dfx_launches.fetch_add(1, std::memory_order_relaxed);             \
-        DFX_CUDA(cudaGetLastError());                                       \
+#define DFX_LAUNCH(kernel, grid, block, smem, stream, ...)                                      \
+    do {                                                                                        \
+        const dim3 _g(grid), _b(block);                                                         \
+        kernel<<<_g, _b, (smem), (stream)>>>(__VA_ARGS__);                                      \
+        g_dfx_launches.fetch_add(1, std::memory_order_relaxed);                                 \
+        cudaError_t _le = cudaGetLastError();                                                   \
+        if (_le != cudaSuccess)                                                                 \
+            throw DfxError{std::string("launch of " #kernel " failed: ") + cudaGetErrorString(_le) + \
+                           " grid=(" + std::to_string(_g.x) + "," + std::to_string(_g.y) + ") block=" + \
+                           std::to_string(_b.x) + " smem=" + std::to_string((size_t)(smem)) + " (" +  \
+                           __FILE__ + ":" + std::to_string(__LINE__) + ")"};                    \
     } while (0)
 
 // grow-only device buffer
 struct DevBuf {
     void* p = nullptr;
     size_t cap = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    DevBuf(DevBuf&& o) noexcept : p(o.p), cap(o.cap) {
+        o.p = nullptr;
+        o.cap = 0;
+    }
+    DevBuf& operator=(DevBuf&& o) noexcept {
+        if (this != &o) {
+            release();
+            p = o.p;
+            cap = o.cap;
+            o.p = nullptr;
+            o.cap = 0;
+        }
+        return *this;
+    }
     ~DevBuf() { release(); }
     void release() {
         if (p) cudaFree(p);

@@ -35,6 +35,12 @@ struct dfx_index {
     int max_points_per_centroid = 256;  // faiss Clustering default
     uint64_t train_seed = 1234;       // faiss Clustering default seed
 
+    // IVF-PQ, M == 32: interleaved block layout for the lane-per-subquantizer scan
+    // (dfx_scan_il.cu).  While `il` is set the row-major payload/tvals/ids are released.
+    bool il = false, il_enabled = true;
+    DevBuf il_codes, il_tvals, il_ids, blk_off;
+    int64_t nblk = 0;
+
     // tensor-core coarse quantizer (dfx_tc.cu): bf16 hi/lo planes and screening workspace
     DevBuf tc_cent, tc_cent_tmp, tc_q, tc_gmin, tc_gmin2, tc_gargc, tc_groups, tc_cand, tc_qn, tc_amb;
     float tc_cmax2 = 0.f;
@@ -104,6 +110,13 @@ void dfx_stats_impl(dfx_index* idx, int64_t* ndis, cudaStream_t st);
 
 void dfx_launch_select_comp(const uint64_t* comp, int64_t nrows, int n, int64_t ld, int k, int32_t* keys,
                             cudaStream_t st);
+
+// ---- dfx_scan_il.cu
+bool dfx_il_wanted(const dfx_index* idx);
+void dfx_pq_rm_to_il(dfx_index* idx, cudaStream_t st);
+void dfx_pq_il_to_rm(dfx_index* idx, cudaStream_t st);
+void dfx_launch_scan_pq_il(dfx_index* idx, int64_t qc, const int32_t* keys, int nprobe, int G, int ngroups,
+                           int k, int cap, uint64_t* part, cudaStream_t st);
 
 // ---- dfx_tc.cu
 bool dfx_tc_supported(int d);

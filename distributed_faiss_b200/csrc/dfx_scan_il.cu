@@ -1,0 +1,205 @@
+// dfx_scan_il.cu -- K4 v2: inverted-list scan of PQ codes, lane-per-subquantizer, on an
+// interleaved code layout (M == 32).
+//
+// Replaces the inner loop of faiss IndexIVFPQ::search (reached from reference
+// distributed_faiss/index.py:257) -- `dis = dis0 + sum_m table[m][code[m]]` over every code of
+// every probed list.
+//
+// Why a second layout: with one vector per lane (v1, dfx_search.cu) the 32 lanes of a warp read
+// table[m][code] for the SAME m and 32 random codes -> random shared-memory bank conflicts
+// (~3.4 wavefronts per lookup), which caps the scan at ~1/3 of the HBM roofline.  Here lane m
+// owns subquantizer m and the table is stored transposed ([code][m]), so the bank of every
+// lookup is the lane id: conflict-free by construction.  The 32 partial values of a vector then
+// sit in 32 different lanes; they are summed by a transposed butterfly (31 shuffles per 32
+// vectors) whose register indices are static because the codes are stored pre-permuted:
+//
+//   block of 32 vectors = 1 KB:  byte [m*32 + r] = code[m] of vector v = r ^ m   (r = 0..31)
+//
+// lane m loads its 32 bytes (2 x LDG.128, the warp reads the KB contiguously), looks up
+// a[r] = tableT[byte r][m], and for off = 16,8,4,2,1:  a[r] += shfl_xor(a[r + off], off) (r < off).
+// Lane m ends with the full sum for vector v = m, added in exactly the halving-tree order of
+// oracle pq_sum (s[i] += s[i+off]).  Lists are padded to whole blocks; padding carries
+// t = +inf so it can never enter a result.
+#include "dfx_internal.h"
+#include "dfx_topk.cuh"
+
+// ------------------------------------------------------------------ layout conversion
+__device__ __forceinline__ int64_t il_list_of_block(const int64_t* __restrict__ blk_off, int64_t nlist, int64_t blk) {
+    int64_t lo = 0, hi = nlist;
+    while (hi - lo > 1) {
+        int64_t mid = (lo + hi) >> 1;
+        if (blk_off[mid] <= blk) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+// row-major (list-sorted) -> interleaved blocks.  one CTA per block.
+__global__ void __launch_bounds__(256)
+pq_rm_to_il_kernel(const int64_t* __restrict__ list_off, const int64_t* __restrict__ blk_off, int64_t nlist,
+                   const uint8_t* __restrict__ codes, const float* __restrict__ tvals,
+                   const int32_t* __restrict__ ids, uint8_t* __restrict__ il_codes, float* __restrict__ il_tvals,
+                   int32_t* __restrict__ il_ids) {
+    const int64_t blk = blockIdx.x;
+    const int64_t l = il_list_of_block(blk_off, nlist, blk);
+    const int64_t base = list_off[l] + (blk - blk_off[l]) * 32, end = list_off[l + 1];
+    for (int b = threadIdx.x; b < 1024; b += 256) {
+        const int m = b >> 5, r = b & 31, v = r ^ m;
+        const int64_t i = base + v;
+        il_codes[blk * 1024 + b] = (i < end) ? codes[i * 32 + m] : (uint8_t)0;
+    }
+    if (threadIdx.x < 32) {
+        const int64_t i = base + threadIdx.x;
+        il_tvals[blk * 32 + threadIdx.x] = (i < end) ? tvals[i] : __int_as_float(0x7f800000);
+        il_ids[blk * 32 + threadIdx.x] = (i < end) ? ids[i] : -1;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+pq_il_to_rm_kernel(const int64_t* __restrict__ list_off, const int64_t* __restrict__ blk_off, int64_t nlist,
+                   const uint8_t* __restrict__ il_codes, const float* __restrict__ il_tvals,
+                   const int32_t* __restrict__ il_ids, uint8_t* __restrict__ codes, float* __restrict__ tvals,
+                   int32_t* __restrict__ ids) {
+    const int64_t blk = blockIdx.x;
+    const int64_t l = il_list_of_block(blk_off, nlist, blk);
+    const int64_t base = list_off[l] + (blk - blk_off[l]) * 32, end = list_off[l + 1];
+    for (int b = threadIdx.x; b < 1024; b += 256) {
+        const int m = b >> 5, r = b & 31, v = r ^ m;
+        const int64_t i = base + v;
+        if (i < end) codes[i * 32 + m] = il_codes[blk * 1024 + b];
+    }
+    if (threadIdx.x < 32) {
+        const int64_t i = base + threadIdx.x;
+        if (i < end) {
+            tvals[i] = il_tvals[blk * 32 + threadIdx.x];
+            ids[i] = il_ids[blk * 32 + threadIdx.x];
+        }
+    }
+}
+
+bool dfx_il_wanted(const dfx_index* idx) {
+    return idx->cfg.kind == DFX_IVF_PQ && idx->M == 32 && idx->il_enabled;
+}
+
+// payload/tvals/ids (row-major, list-sorted) -> il_* ; frees the row-major arrays
+void dfx_pq_rm_to_il(dfx_index* idx, cudaStream_t st) {
+    if (idx->il || !dfx_il_wanted(idx)) return;
+    const int64_t nlist = idx->cfg.nlist;
+    std::vector<int64_t> h_blk((size_t)nlist + 1);
+    h_blk[0] = 0;
+    for (int64_t l = 0; l < nlist; l++)
+        h_blk[(size_t)l + 1] = h_blk[(size_t)l] + dfx_ceil_div(idx->h_list_off[(size_t)l + 1] - idx->h_list_off[(size_t)l], 32);
+    const int64_t nblk = h_blk[(size_t)nlist];
+    idx->blk_off.reserve((size_t)(nlist + 1) * 8);
+    DFX_CUDA(cudaMemcpyAsync(idx->blk_off.p, h_blk.data(), (size_t)(nlist + 1) * 8, cudaMemcpyHostToDevice, st));
+    idx->il_codes.reserve((size_t)std::max<int64_t>(nblk, 1) * 1024);
+    idx->il_tvals.reserve((size_t)std::max<int64_t>(nblk, 1) * 32 * 4);
+    idx->il_ids.reserve((size_t)std::max<int64_t>(nblk, 1) * 32 * 4);
+    if (nblk > 0)
+        DFX_LAUNCH(pq_rm_to_il_kernel, (unsigned)nblk, 256, 0, st, idx->list_off.as<int64_t>(),
+                   idx->blk_off.as<int64_t>(), nlist, idx->payload.as<uint8_t>(), idx->tvals.as<float>(),
+                   idx->ids.as<int32_t>(), idx->il_codes.as<uint8_t>(), idx->il_tvals.as<float>(),
+                   idx->il_ids.as<int32_t>());
+    DFX_CUDA(cudaStreamSynchronize(st));  // h_blk is on the stack of this call
+    idx->payload.release();
+    idx->tvals.release();
+    idx->ids.release();
+    idx->nblk = nblk;
+    idx->il = true;
+    idx->inv_valid = false;
+}
+
+// il_* -> payload/tvals/ids (row-major); frees the interleaved arrays
+void dfx_pq_il_to_rm(dfx_index* idx, cudaStream_t st) {
+    if (!idx->il) return;
+    const int64_t n = idx->n_sorted;
+    idx->payload.reserve((size_t)std::max<int64_t>(n, 1) * 32);
+    idx->tvals.reserve((size_t)std::max<int64_t>(n, 1) * 4);
+    idx->ids.reserve((size_t)std::max<int64_t>(n, 1) * 4);
+    if (idx->nblk > 0)
+        DFX_LAUNCH(pq_il_to_rm_kernel, (unsigned)idx->nblk, 256, 0, st, idx->list_off.as<int64_t>(),
+                   idx->blk_off.as<int64_t>(), idx->cfg.nlist, idx->il_codes.as<uint8_t>(),
+                   idx->il_tvals.as<float>(), idx->il_ids.as<int32_t>(), idx->payload.as<uint8_t>(),
+                   idx->tvals.as<float>(), idx->ids.as<int32_t>());
+    DFX_CUDA(cudaStreamSynchronize(st));
+    idx->il_codes.release();
+    idx->il_tvals.release();
+    idx->il_ids.release();
+    idx->nblk = 0;
+    idx->il = false;
+    idx->inv_valid = false;
+}
+
+// ------------------------------------------------------------------ the scan
+// lutT: [nq][256][32] (transposed table, written by pq_prep_kernel)
+constexpr int IL_THREADS = 256;  // 8 warps: 4 CTAs/SM = 32 warps/SM (the 64-register limit)
+__global__ void __launch_bounds__(IL_THREADS)
+scan_pq_il_kernel(const float* __restrict__ lutT, const float* __restrict__ dis0, const int32_t* __restrict__ keys,
+                  int nprobe, int G, int ngroups, const int64_t* __restrict__ blk_off,
+                  const uint4* __restrict__ il_codes, const float* __restrict__ il_tvals,
+                  const int32_t* __restrict__ il_ids, int k, int cap, uint64_t* __restrict__ part) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* s_lut = reinterpret_cast<float*>(smem_raw);                       // [256][32]
+    uint64_t* s_buf = reinterpret_cast<uint64_t*>(smem_raw + 256 * 32 * 4);  // 8 warps x cap
+    const int64_t q = blockIdx.x / ngroups;
+    const int g = blockIdx.x % ngroups;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    {
+        const float4* src = reinterpret_cast<const float4*>(lutT + q * 8192);
+        float4* dst = reinterpret_cast<float4*>(s_lut);
+        for (int i = tid; i < 2048; i += IL_THREADS) dst[i] = src[i];
+    }
+    WarpTopK wt;
+    wt.init(s_buf + (size_t)warp * cap, cap, k);
+    __syncthreads();
+    const char* lut_lane = reinterpret_cast<const char*>(s_lut) + lane * 4;  // + code*128 per lookup
+
+    const int p_end = min(nprobe, (g + 1) * G);
+    for (int p = g * G; p < p_end; p++) {
+        const int l = keys[q * nprobe + p];
+        if (l < 0) continue;
+        const float d0 = dis0[q * nprobe + p];
+        const int64_t bend = blk_off[l + 1];
+        int64_t b = blk_off[l] + warp;
+        uint4 c0, c1;
+        if (b < bend) {
+            c0 = __ldg(il_codes + b * 64 + lane * 2);
+            c1 = __ldg(il_codes + b * 64 + lane * 2 + 1);
+        }
+        while (b < bend) {
+            const uint32_t w[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+            const float tv = __ldg(il_tvals + b * 32 + lane);
+            const int64_t bn = b + IL_THREADS / 32;
+            if (bn < bend) {  // prefetch the next block of this warp
+                c0 = __ldg(il_codes + bn * 64 + lane * 2);
+                c1 = __ldg(il_codes + bn * 64 + lane * 2 + 1);
+            }
+            float a[32];
+#pragma unroll
+            for (int r = 0; r < 32; r++) {
+                const uint32_t code = (w[r >> 2] >> (8 * (r & 3))) & 255u;
+                a[r] = *reinterpret_cast<const float*>(lut_lane + code * 128);
+            }
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) {
+#pragma unroll
+                for (int r = 0; r < off; r++) a[r] = a[r] + __shfl_xor_sync(0xffffffffu, a[r + off], off);
+            }
+            const float v = d0 + (tv + a[0]);  // vector `lane` of this block; padding has tv = +inf
+            uint32_t sec = 0;
+            const bool want = wt.admits(v, [&] { return (uint32_t)__ldg(il_ids + b * 32 + lane); }, sec);
+            wt.push_lanes(want, v, sec);
+            b = bn;
+        }
+    }
+    cta_merge_and_write<IL_THREADS>(wt, s_buf, cap, k, part + ((int64_t)q * ngroups + g) * k);
+}
+
+void dfx_launch_scan_pq_il(dfx_index* idx, int64_t qc, const int32_t* keys, int nprobe, int G, int ngroups, int k,
+                           int cap, uint64_t* part, cudaStream_t st) {
+    const size_t smem = (size_t)256 * 32 * 4 + (size_t)(IL_THREADS / 32) * cap * 8;
+    auto kern = scan_pq_il_kernel;
+    DFX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    DFX_LAUNCH(kern, (unsigned)(qc * ngroups), IL_THREADS, smem, st, idx->w_lut.as<float>(), idx->w_dis0.as<float>(), keys,
+               nprobe, G, ngroups, idx->blk_off.as<int64_t>(), idx->il_codes.as<uint4>(), idx->il_tvals.as<float>(),
+               idx->il_ids.as<int32_t>(), k, cap, part);
+}

@@ -12,6 +12,7 @@
 // Arithmetic orders are the canonical ones of oracle/dfx_oracle.c (bit-exact parity).
 #include "dfx_internal.h"
 #include "dfx_select.cuh"
+#include "dfx_topk.cuh"
 
 // =====================================================================================
 // K1a: values GEMM (fp32 FFMA).  acc = fmaf(q[k], x[k], acc), k ascending.
@@ -187,12 +188,16 @@ void dfx_launch_select_comp(const uint64_t* comp, int64_t nrows, int n, int64_t 
 // =====================================================================================
 // K3: pq_prep.  lut[q][m][j] = -2 * ip_seq(q_m, P[m][j]);  dis0[q][p] = warp-dot ||q - c||^2
 // =====================================================================================
+// transposed != 0 (M == 32): the table is written as lut[q][j][m] for the lane-per-subquantizer
+// scan (dfx_scan_il.cu); it is staged through padded shared memory so both the codebook reads
+// and the global writes stay coalesced.
 __global__ void __launch_bounds__(256)
 pq_prep_kernel(const float* __restrict__ Q, int d, int M, int ksub, int dsub,
                const float* __restrict__ codebooks, const float* __restrict__ cent,
                const int32_t* __restrict__ keys, int nprobe, float* __restrict__ lut,
-               float* __restrict__ dis0) {
+               float* __restrict__ dis0, int transposed) {
     extern __shared__ float s_q[];
+    float* s_t = s_q + ((d + 3) / 4) * 4;  // transposed mode: [M][ksub + 1]
     const int64_t q = blockIdx.x;
     for (int i = threadIdx.x; i < d; i += blockDim.x) s_q[i] = Q[q * d + i];
     __syncthreads();
@@ -204,7 +209,15 @@ pq_prep_kernel(const float* __restrict__ Q, int d, int M, int ksub, int dsub,
             const float* qm = s_q + m * dsub;
             float acc = 0.f;
             for (int t = 0; t < dsub; t++) acc = __fmaf_rn(qm[t], p[t], acc);
-            lut[q * tot + idx] = -2.f * acc;
+            if (transposed) s_t[m * (ksub + 1) + (idx - m * ksub)] = -2.f * acc;
+            else lut[q * tot + idx] = -2.f * acc;
+        }
+        if (transposed) {
+            __syncthreads();
+            for (int o = threadIdx.x; o < tot; o += blockDim.x) {
+                const int j = o / M, m = o - j * M;
+                lut[q * tot + o] = s_t[m * (ksub + 1) + j];
+            }
         }
     }
     if (dis0) {
@@ -231,97 +244,8 @@ pq_prep_kernel(const float* __restrict__ Q, int d, int M, int ksub, int dsub,
 }
 
 // =====================================================================================
-// per-warp candidate set: keeps the k best composites seen so far in shared memory.
-// buf has CAP = 2*KP slots (KP = pow2 >= max(k,32)); when it cannot take another 32
-// entries it is bitonic-sorted by the warp and cut back to k; thr = current k-th value.
-// =====================================================================================
-struct WarpTopK {
-    uint64_t* buf;
-    int cap, k, cnt;
-    float thr;         // value of the current k-th best (+inf until k candidates are held)
-    uint32_t thr_sec;  // its secondary key: an equal value is only admitted with a smaller one
-    __device__ __forceinline__ void init(uint64_t* b, int cap_, int k_) {
-        buf = b;
-        cap = cap_;
-        k = k_;
-        cnt = 0;
-        thr = __int_as_float(0x7f800000);  // +inf
-        thr_sec = DFX_SEC_NONE;
-    }
-    // does (v, sec) beat the current k-th best?  `sec` is fetched lazily: only on a value tie
-    template <class SecFn>
-    __device__ __forceinline__ bool admits(float v, SecFn sec_of, uint32_t& sec) const {
-        v = v + 0.0f;
-        if (v < thr) {
-            sec = sec_of();
-            return true;
-        }
-        if (v == thr) {
-            sec = sec_of();
-            return sec < thr_sec;
-        }
-        return false;
-    }
-    __device__ __forceinline__ void sort_and_cut() {
-        const int lane = threadIdx.x & 31;
-        for (int e = cnt + lane; e < cap; e += 32) buf[e] = DFX_COMP_NONE;
-        __syncwarp();
-        for (int size = 2; size <= cap; size <<= 1) {
-            for (int stride = size >> 1; stride > 0; stride >>= 1) {
-                for (int i = lane; i < (cap >> 1); i += 32) {
-                    int pos = 2 * i - (i & (stride - 1));
-                    int partner = pos + stride;
-                    bool up = ((pos & size) == 0);
-                    uint64_t a = buf[pos], b = buf[partner];
-                    if ((a > b) == up) {
-                        buf[pos] = b;
-                        buf[partner] = a;
-                    }
-                }
-                __syncwarp();
-            }
-        }
-        if (cnt > k) cnt = k;
-        if (cnt == k) {
-            const uint64_t kth = buf[k - 1];
-            thr = dfx_key2f((uint32_t)(kth >> 32));
-            thr_sec = (uint32_t)kth;
-        }
-        __syncwarp();
-    }
-    // each lane may contribute one candidate (want = lane has one)
-    __device__ __forceinline__ void push_lanes(bool want, float v, uint32_t sec) {
-        unsigned mask = __ballot_sync(0xffffffffu, want);
-        if (mask == 0) return;
-        const int lane = threadIdx.x & 31;
-        if (want) buf[cnt + __popc(mask & ((1u << lane) - 1u))] = dfx_comp(v, sec);
-        cnt += __popc(mask);
-        __syncwarp();
-        if (cnt > cap - 32) sort_and_cut();
-    }
-    // warp-uniform single candidate
-    __device__ __forceinline__ void push_uniform(float v, uint32_t sec) {
-        if ((threadIdx.x & 31) == 0) buf[cnt] = dfx_comp(v, sec);
-        cnt += 1;
-        __syncwarp();
-        if (cnt > cap - 32) sort_and_cut();
-    }
-};
-
-// merges the per-warp sets of a CTA and writes k composites (NONE padded) to out
-template <int THREADS>
-__device__ __forceinline__ void cta_merge_and_write(WarpTopK& wt, uint64_t* s_buf, int cap, int k,
-                                                    uint64_t* out) {
-    wt.sort_and_cut();  // leaves [cnt, cap) == NONE
-    __syncthreads();
-    constexpr int NW = THREADS / 32;
-    dfx_block_bitonic_sort<THREADS>(s_buf, NW * cap);
-    for (int j = threadIdx.x; j < k; j += THREADS) out[j] = s_buf[j];
-}
-
-// =====================================================================================
 // K4: scan_pq.  one CTA = (query, group of G consecutive probes).  lane-per-vector:
-//   v = dis0 + (t + S),  S = (a0+a1)+(a2+a3), a_i = sum over m == i (mod 4) of lut[m][code_m]
+//   v = dis0 + (t + S),  S = halving-tree sum of lut[m][code_m] (oracle pq_sum)
 // =====================================================================================
 template <int MT>
 __global__ void __launch_bounds__(128)
@@ -358,7 +282,9 @@ scan_pq_kernel(const float* __restrict__ lut, const float* __restrict__ dis0,
             const bool valid = i < end;
             float v = 0.f;
             if (valid) {
-                float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+                // table values of this vector, then the canonical halving tree (oracle pq_sum)
+                constexpr int P = (MT > 0) ? MT : 64;  // MT is a power of two when > 0
+                float val[P];
                 if (MT > 0 && (MT % 16) == 0) {
                     const uint4* cp = reinterpret_cast<const uint4*>(codes + i * (int64_t)M);
 #pragma unroll
@@ -368,25 +294,33 @@ scan_pq_kernel(const float* __restrict__ lut, const float* __restrict__ dis0,
 #pragma unroll
                         for (int w = 0; w < 4; w++) {
                             const int m = w4 * 16 + w * 4;
-                            a0 = a0 + s_lut[(m + 0) * ksub + (wv[w] & 255u)];
-                            a1 = a1 + s_lut[(m + 1) * ksub + ((wv[w] >> 8) & 255u)];
-                            a2 = a2 + s_lut[(m + 2) * ksub + ((wv[w] >> 16) & 255u)];
-                            a3 = a3 + s_lut[(m + 3) * ksub + (wv[w] >> 24)];
+                            val[m + 0] = s_lut[(m + 0) * ksub + (wv[w] & 255u)];
+                            val[m + 1] = s_lut[(m + 1) * ksub + ((wv[w] >> 8) & 255u)];
+                            val[m + 2] = s_lut[(m + 2) * ksub + ((wv[w] >> 16) & 255u)];
+                            val[m + 3] = s_lut[(m + 3) * ksub + (wv[w] >> 24)];
                         }
                     }
                 } else {
                     const uint32_t* cp = reinterpret_cast<const uint32_t*>(codes + i * (int64_t)M);
-                    for (int w = 0; w < M / 4; w++) {
-                        uint32_t c = __ldg(cp + w);
+#pragma unroll
+                    for (int w = 0; w < P / 4; w++) {
                         const int m = w * 4;
-                        a0 = a0 + s_lut[(m + 0) * ksub + (c & 255u)];
-                        a1 = a1 + s_lut[(m + 1) * ksub + ((c >> 8) & 255u)];
-                        a2 = a2 + s_lut[(m + 2) * ksub + ((c >> 16) & 255u)];
-                        a3 = a3 + s_lut[(m + 3) * ksub + (c >> 24)];
+                        if (m < M) {
+                            uint32_t c = __ldg(cp + w);
+                            val[m + 0] = s_lut[(m + 0) * ksub + (c & 255u)];
+                            val[m + 1] = s_lut[(m + 1) * ksub + ((c >> 8) & 255u)];
+                            val[m + 2] = s_lut[(m + 2) * ksub + ((c >> 16) & 255u)];
+                            val[m + 3] = s_lut[(m + 3) * ksub + (c >> 24)];
+                        } else {
+                            val[m + 0] = val[m + 1] = val[m + 2] = val[m + 3] = 0.f;
+                        }
                     }
                 }
-                const float S = (a0 + a1) + (a2 + a3);
-                v = d0 + (__ldg(tvals + i) + S);
+#pragma unroll
+                for (int off = P / 2; off >= 1; off >>= 1)
+#pragma unroll
+                    for (int r = 0; r < off; r++) val[r] = val[r] + val[r + off];
+                v = d0 + (__ldg(tvals + i) + val[0]);
             }
             uint32_t sec = 0;
             const bool want = valid && wt.admits(v, [&] { return (uint32_t)__ldg(ids + i); }, sec);
@@ -652,9 +586,12 @@ void dfx_search_impl(dfx_index* idx, int64_t nq, const float* d_x, int64_t k64, 
     const int cmetric = idx->cfg.metric;  // coarse quantizer metric
     const int smetric = (kind == DFX_IVF_FLAT) ? idx->cfg.metric : DFX_METRIC_L2;
 
-    int64_t QC = (32ll << 20) / nlist;
+    // query chunk: bounds the workspace (values matrix on the FFMA coarse path, tables and
+    // partial results otherwise)
+    const bool use_tc = idx->tc_enabled && idx->tc_ready && nlist >= 1024 && nprobe <= 512;
+    int64_t QC = use_tc ? 8192 : (32ll << 20) / nlist;
     if (QC < 1) QC = 1;
-    if (QC > 4096) QC = 4096;
+    if (QC > 8192) QC = 8192;
     if (QC > nq) QC = nq;
     const int KP = dfx_next_pow2(k < 32 ? 32 : k);
     const int cap = 2 * KP;
@@ -667,7 +604,7 @@ void dfx_search_impl(dfx_index* idx, int64_t nq, const float* d_x, int64_t k64, 
         const float* xq = d_x + q0 * d;
         int32_t* keys = keys_all + q0 * nprobe;
         // K1: coarse quantizer -- tensor cores (screen) + canonical fp32 (decide), or plain FFMA
-        if (idx->tc_enabled && idx->tc_ready && nlist >= 1024 && nprobe <= 512) {
+        if (use_tc) {
             dfx_tc_coarse_search(idx, xq, qc, nprobe, keys, st);
         } else {
             idx->w_vals.reserve((size_t)QC * nlist * 4);
@@ -696,9 +633,17 @@ void dfx_search_impl(dfx_index* idx, int64_t nq, const float* d_x, int64_t k64, 
             const int M = idx->M, ksub = idx->ksub;
             idx->w_lut.reserve((size_t)qc * M * ksub * 4);
             idx->w_dis0.reserve((size_t)qc * nprobe * 4);
-            DFX_LAUNCH(pq_prep_kernel, (unsigned)qc, 256, (size_t)d * 4, st, xq, d, M, ksub, idx->dsub,
+            const int il = idx->il ? 1 : 0;
+            const size_t prep_smem = (size_t)((d + 3) / 4) * 16 + (il ? (size_t)M * (ksub + 1) * 4 : 0);
+            if (prep_smem > 48 * 1024)
+                DFX_CUDA(cudaFuncSetAttribute(pq_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              (int)prep_smem));
+            DFX_LAUNCH(pq_prep_kernel, (unsigned)qc, 256, prep_smem, st, xq, d, M, ksub, idx->dsub,
                        idx->codebooks.as<float>(), idx->centroids.as<float>(), keys, nprobe,
-                       idx->w_lut.as<float>(), idx->w_dis0.as<float>());
+                       idx->w_lut.as<float>(), idx->w_dis0.as<float>(), il);
+            if (il) {
+                dfx_launch_scan_pq_il(idx, qc, keys, nprobe, G, ngroups, k, cap, part, st);
+            } else {
             const size_t smem = (size_t)M * ksub * 4 + (size_t)4 * cap * 8;
 #define DFX_SCAN_PQ(MT)                                                                          \
     do {                                                                                         \
@@ -713,8 +658,10 @@ void dfx_search_impl(dfx_index* idx, int64_t nq, const float* d_x, int64_t k64, 
             if (M == 32) DFX_SCAN_PQ(32);
             else if (M == 64) DFX_SCAN_PQ(64);
             else if (M == 16) DFX_SCAN_PQ(16);
-            else DFX_SCAN_PQ(0);
+            else if (M == 8) DFX_SCAN_PQ(8);
+            else DFX_SCAN_PQ(0);  // any other M <= 64: values padded to 64 with +0
 #undef DFX_SCAN_PQ
+            }
         } else {
             const int dq = (kind == DFX_IVF_SQ16) ? 2 * d : d;
             const size_t smem = (((size_t)dq * 4 + 15) / 16) * 16 + (size_t)4 * cap * 8;

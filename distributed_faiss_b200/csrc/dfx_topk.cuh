@@ -1,0 +1,94 @@
+// dfx_topk.cuh -- per-warp / per-CTA k-selection used by the inverted-list scan kernels.
+#pragma once
+#include "dfx_common.cuh"
+#include "dfx_select.cuh"
+
+// =====================================================================================
+// per-warp candidate set: keeps the k best composites seen so far in shared memory.
+// buf has CAP = 2*KP slots (KP = pow2 >= max(k,32)); when it cannot take another 32
+// entries it is bitonic-sorted by the warp and cut back to k; thr = current k-th value.
+// =====================================================================================
+struct WarpTopK {
+    uint64_t* buf;
+    int cap, k, cnt;
+    float thr;         // value of the current k-th best (+inf until k candidates are held)
+    uint32_t thr_sec;  // its secondary key: an equal value is only admitted with a smaller one
+    __device__ __forceinline__ void init(uint64_t* b, int cap_, int k_) {
+        buf = b;
+        cap = cap_;
+        k = k_;
+        cnt = 0;
+        thr = __int_as_float(0x7f800000);  // +inf
+        thr_sec = DFX_SEC_NONE;
+    }
+    // does (v, sec) beat the current k-th best?  `sec` is fetched lazily: only on a value tie
+    template <class SecFn>
+    __device__ __forceinline__ bool admits(float v, SecFn sec_of, uint32_t& sec) const {
+        v = v + 0.0f;
+        if (v < thr) {
+            sec = sec_of();
+            return true;
+        }
+        if (v == thr) {
+            sec = sec_of();
+            return sec < thr_sec;
+        }
+        return false;
+    }
+    __device__ __forceinline__ void sort_and_cut() {
+        const int lane = threadIdx.x & 31;
+        for (int e = cnt + lane; e < cap; e += 32) buf[e] = DFX_COMP_NONE;
+        __syncwarp();
+        for (int size = 2; size <= cap; size <<= 1) {
+            for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                for (int i = lane; i < (cap >> 1); i += 32) {
+                    int pos = 2 * i - (i & (stride - 1));
+                    int partner = pos + stride;
+                    bool up = ((pos & size) == 0);
+                    uint64_t a = buf[pos], b = buf[partner];
+                    if ((a > b) == up) {
+                        buf[pos] = b;
+                        buf[partner] = a;
+                    }
+                }
+                __syncwarp();
+            }
+        }
+        if (cnt > k) cnt = k;
+        if (cnt == k) {
+            const uint64_t kth = buf[k - 1];
+            thr = dfx_key2f((uint32_t)(kth >> 32));
+            thr_sec = (uint32_t)kth;
+        }
+        __syncwarp();
+    }
+    // each lane may contribute one candidate (want = lane has one)
+    __device__ __forceinline__ void push_lanes(bool want, float v, uint32_t sec) {
+        unsigned mask = __ballot_sync(0xffffffffu, want);
+        if (mask == 0) return;
+        const int lane = threadIdx.x & 31;
+        if (want) buf[cnt + __popc(mask & ((1u << lane) - 1u))] = dfx_comp(v, sec);
+        cnt += __popc(mask);
+        __syncwarp();
+        if (cnt > cap - 32) sort_and_cut();
+    }
+    // warp-uniform single candidate
+    __device__ __forceinline__ void push_uniform(float v, uint32_t sec) {
+        if ((threadIdx.x & 31) == 0) buf[cnt] = dfx_comp(v, sec);
+        cnt += 1;
+        __syncwarp();
+        if (cnt > cap - 32) sort_and_cut();
+    }
+};
+
+// merges the per-warp sets of a CTA and writes k composites (NONE padded) to out
+template <int THREADS>
+__device__ __forceinline__ void cta_merge_and_write(WarpTopK& wt, uint64_t* s_buf, int cap, int k,
+                                                    uint64_t* out) {
+    wt.sort_and_cut();  // leaves [cnt, cap) == NONE
+    __syncthreads();
+    constexpr int NW = THREADS / 32;
+    dfx_block_bitonic_sort<THREADS>(s_buf, NW * cap);
+    for (int j = threadIdx.x; j < k; j += THREADS) out[j] = s_buf[j];
+}
+

@@ -35,10 +35,18 @@ class CudaBackend:
     def search(self, shard, x_t, k):
         return shard.search_dev(x_t, k)
 
-    def map_ids(self, ids_t, table_t):
+    def search_into(self, shard, x_t, k, D_out, I_out, table_t):
+        """search one shard and leave (D, caller ids) in the given [nq,k] slices, no extra copies"""
+        if table_t is None:
+            shard.search_dev(x_t, k, D_out, I_out)
+        else:
+            _, I_local = shard.search_dev(x_t, k, D_out, None)
+            self.map_ids(I_local, table_t, I_out)
+
+    def map_ids(self, ids_t, table_t, out_t=None):
         from . import engine
 
-        return engine.map_ids_dev(ids_t, table_t)
+        return engine.map_ids_dev(ids_t, table_t, out_t)
 
     def merge(self, D_t, I_t, negate):
         from . import engine
@@ -99,11 +107,7 @@ class ShardGroup:
         D_loc = torch.empty((S_loc, nq, k), dtype=torch.float32, device=x_t.device)
         I_loc = torch.empty((S_loc, nq, k), dtype=torch.int64, device=x_t.device)
         for j, shard in enumerate(self.shards):
-            Dj, Ij = self.backend.search(shard, x_t, k)
-            if self.id_tables[j] is not None:
-                Ij = self.backend.map_ids(Ij, self.id_tables[j])
-            D_loc[j].copy_(Dj)
-            I_loc[j].copy_(Ij)
+            self.backend.search_into(shard, x_t, k, D_loc[j], I_loc[j], self.id_tables[j])
         if self.world > 1:
             D_all = torch.empty((self.world * S_loc, nq, k), dtype=torch.float32, device=x_t.device)
             I_all = torch.empty((self.world * S_loc, nq, k), dtype=torch.int64, device=x_t.device)

@@ -69,7 +69,9 @@ int dfx_train_dev(dfx_index *idx, int64_t n, const float *d_x, void *stream);
 int dfx_add_dev(dfx_index *idx, int64_t n, const float *d_x, void *stream);
 /* training knobs: "kmeans_niter" (default 25), "max_points_per_centroid" (256),
  * "train_seed" (1234) -- the faiss Clustering defaults; "tensor_cores" (1): 0 forces the plain
- * fp32 FFMA coarse quantizer instead of the tcgen05 screening path (same results) */
+ * fp32 FFMA coarse quantizer instead of the tcgen05 screening path (same results);
+ * "interleaved" (1): 0 keeps IVF-PQ codes row-major and scans them one vector per lane
+ * instead of the interleaved lane-per-subquantizer layout (same results) */
 int dfx_set_param(dfx_index *idx, const char *name, double value);
 /* pre-size the shard for n_total vectors (optional; avoids regrowth while bulk loading) */
 int dfx_reserve(dfx_index *idx, int64_t n_total);

@@ -34,8 +34,8 @@
  *   warp-dot: 32 partial sums, lane j owns k = 128*i + 4*j + t (t=0..3),
  *             then a butterfly (xor 16,8,4,2,1) of plain adds (scan-shaped
  *             paths: IVF-Flat, IVF-SQ, exact ||q-c||^2)
- *   pq-sum  : four accumulators a_i over m == i (mod 4), m ascending;
- *             S = (a0+a1)+(a2+a3); dist = dis0 + (t + S)
+ *   pq-sum  : the M table values reduced by a halving tree (s[i] += s[i+off], off = P/2..1,
+ *             P = M rounded up to a power of two); dist = dis0 + (t + S)
  * Every result set is ordered by the TOTAL order (value asc, id asc) where
  * value = distance (L2) or -inner_product (IP).
  *
@@ -418,10 +418,17 @@ void orc_pq_tvals(int d, int M, int ksub, const float *codebooks, const float *c
     }
 }
 
+/* pq-sum canonical order: the M table values are padded with +0 to P = next power of two and
+ * reduced by a halving tree: for off = P/2, P/4, ..., 1: s[i] = s[i] + s[i+off] (i < off).
+ * (This is the order in which a warp butterfly adds them on the GPU.) */
 static inline float pq_sum(const float *lut, const uint8_t *code, int M, int ksub) {
-    float a[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int m = 0; m < M; m++) a[m & 3] = a[m & 3] + lut[m * ksub + code[m]];
-    return (a[0] + a[1]) + (a[2] + a[3]);
+    float s[256];
+    int P = 1;
+    while (P < M) P <<= 1;
+    for (int m = 0; m < P; m++) s[m] = (m < M) ? lut[m * ksub + code[m]] : 0.f;
+    for (int off = P >> 1; off >= 1; off >>= 1)
+        for (int i = 0; i < off; i++) s[i] = s[i] + s[i + off];
+    return s[0];
 }
 
 int orc_ivfpq_search(int coarse_metric, int d, int64_t nlist, const float *cent, int M, int ksub,

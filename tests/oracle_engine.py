@@ -46,6 +46,11 @@ class OracleBackend:
         D, I = shard.search(x_t.numpy(), k)
         return torch.from_numpy(D), torch.from_numpy(I)
 
+    def search_into(self, shard, x_t, k, D_out, I_out, table_t):
+        D, I = self.search(shard, x_t, k)
+        D_out.copy_(D)
+        I_out.copy_(I if table_t is None else self.map_ids(I, table_t))
+
     def map_ids(self, ids_t, table_t):
         import torch
 

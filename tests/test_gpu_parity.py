@@ -365,3 +365,41 @@ def test_tensor_core_assign_matches_oracle():
     assert np.array_equal(o.list_off, st["list_off"])
     assert np.array_equal(o.ids, st["ids"])
     assert np.array_equal(o.codes, st["codes"])
+
+
+def test_interleaved_and_row_major_pq_layouts_agree():
+    """IVF-PQ, M=32: the interleaved lane-per-subquantizer scan (default) and the row-major
+    lane-per-vector scan return the same bits as the oracle; export/import/reconstruct work in
+    both layouts and across incremental adds."""
+    from oracle import oracle as O
+
+    E = _engine()
+    rs = np.random.RandomState(14)
+    d, nlist, M, n = 128, 48, 32, 30_011            # odd sizes: partial blocks in most lists
+    xb = clustered(rs, n, d, ncl=60)
+    xq = xb[:37] + 0.01 * rs.randn(37, d).astype(np.float32)
+    g = E.GpuIndex(E.KIND_IVF_PQ, d, L2, nlist=nlist, pq_m=M)
+    g.train(xb[:8000])
+    g.add(xb[:10_000]); g.nprobe = 6
+    D0, I0 = g.search(xq, 10)                        # builds the interleaved form
+    g.add(xb[10_000:])                               # incremental add on top of it
+    o = O.OracleIVFPQ(d, nlist, M, 8, coarse_metric=L2)
+    o.set_state(g.get_state())                       # export de-interleaves
+    assert o.ntotal == n
+    for nprobe, k in ((6, 10), (nlist, 100), (1, 1)):
+        g.nprobe = nprobe; o.nprobe = nprobe
+        Do, Io = o.search(xq, k)
+        g.set_param("interleaved", 1)
+        _assert_same(*g.search(xq, k), Do, Io, f"interleaved nprobe={nprobe}")
+        ids = np.array([0, 5, n - 1, -1, 12345], dtype=np.int64)
+        R_il = g.reconstruct_rows(ids)
+        g.set_param("interleaved", 0)
+        _assert_same(*g.search(xq, k), Do, Io, f"row-major nprobe={nprobe}")
+        R_rm = g.reconstruct_rows(ids)
+        assert np.array_equal(R_il[[0, 1, 2, 4]], R_rm[[0, 1, 2, 4]]) and np.isnan(R_il[3]).all()
+        assert np.allclose(R_il[[0, 1, 2, 4]], o.reconstruct_rows(ids)[[0, 1, 2, 4]], rtol=0, atol=1e-6)
+    g.set_param("interleaved", 1)
+    g2 = E.GpuIndex(E.KIND_IVF_PQ, d, L2, nlist=nlist, pq_m=M)
+    g2.set_state(o.get_state())                      # import interleaves
+    g2.nprobe = 6; o.nprobe = 6
+    _assert_same(*g2.search(xq, 10), *o.search(xq, 10), "imported, interleaved")
