@@ -210,17 +210,25 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------
-def cpu_baseline(shard_idx_obj, xq_np, nprobe, nq_cpu, n_shards_total):
-    """The reference's CPU path (oracle restatement), all host threads, on ONE shard of the
-    workload; system QPS = shard QPS / n_shards (the same host serves every shard, SURVEY 8d)."""
+def make_cpu_oracle(shard_idx_obj):
+    """ship ONE shard (codes, ids, centroids, codebooks) to the host and wrap it in the oracle"""
     from oracle import oracle as O
 
     st = shard_idx_obj.get_state()
     o = O.OracleIVFPQ(D, st["nlist"], PQ_M, 8, coarse_metric=O.METRIC_L2)
     o.set_state(st, recompute_tvals=False)
+    return o
+
+
+def cpu_baseline(o, xq_np, nprobe, nq_cpu, n_shards_total, warm=True):
+    """The reference's CPU path (oracle restatement), all host threads, on ONE shard of the
+    workload; system QPS = shard QPS / n_shards (the same host serves every shard, SURVEY 8d)."""
+    from oracle import oracle as O
+
     o.nprobe = nprobe
     q = xq_np[:nq_cpu]
-    o.search(q[:32], K)  # warm-up
+    if warm:
+        o.search(q[:32], K)
     t0 = time.perf_counter()
     Do, Io = o.search(q, K)
     dt = time.perf_counter() - t0
@@ -262,9 +270,14 @@ def main():
 
     log("imports done")
 
-    rank, local_rank, world = spmd.init_process_group_from_env()
-    if args.impl == "reference" and rank != 0:
-        return 0
+    if args.impl == "reference":
+        # CPU arm: rank 0 alone runs and prints; no process group is needed
+        if int(os.environ.get("RANK", "0")) != 0:
+            return 0
+        rank, local_rank, world = 0, int(os.environ.get("LOCAL_RANK", "0")), 1
+        torch.cuda.set_device(local_rank % max(torch.cuda.device_count(), 1))
+    else:
+        rank, local_rank, world = spmd.init_process_group_from_env()
     assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback)"
     assert NSHARDS % world == 0, "--gpus must divide 8"
     dist = torch.distributed
@@ -309,12 +322,16 @@ def main():
 
     # ---------------- reference arm: CPU only
     if args.impl == "reference":
-        nprobe = args.nprobe or 32
+        # same nprobe as the GPU arm's recall gate selects for this size (measured: bench logs in
+        # profiles/; the GPU arm re-measures and reports its own value in config.nprobe)
+        nprobe = args.nprobe or (8 if nvec >= 500_000_000 else 4)
         xq_np = xq.cpu().numpy()
+        orc = make_cpu_oracle(shards[0])
+        log("shard 0 exported to the host oracle")
         vals = []
         for it in range(args.warmup + args.steps):
-            cb = cpu_baseline(shards[0], xq_np[(it * args.cpu_queries) % (args.nq_pool - args.cpu_queries):], nprobe,
-                              args.cpu_queries, NSHARDS)
+            off = (it * args.cpu_queries) % max(1, args.nq_pool - args.cpu_queries)
+            cb = cpu_baseline(orc, xq_np[off:], nprobe, args.cpu_queries, NSHARDS, warm=(it == 0))
             if it >= args.warmup:
                 vals.append(cb["value"])
         cb.pop("_D"), cb.pop("_I")
@@ -446,7 +463,7 @@ def main():
     log("e2e + sweep done")
     cb = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        cb = cpu_baseline(shards[0], xq.cpu().numpy(), nprobe, args.cpu_queries, NSHARDS)
+        cb = cpu_baseline(make_cpu_oracle(shards[0]), xq.cpu().numpy(), nprobe, args.cpu_queries, NSHARDS)
         # cross-check on the way: the GPU shard and the oracle agree bit for bit on this sample
         shards[0].nprobe = nprobe
         Dg, Ig = shards[0].search(xq[:args.cpu_queries].cpu().numpy(), K)

@@ -356,6 +356,54 @@ __device__ __forceinline__ float screen_tol(float qn2, float cmax2) {
     return 1e-4f * sqrtf(qn2 * cmax2) + 1e-30f;
 }
 
+// The G smallest group minima of a row, ascending by (value, group), for any G <= ng: one warp
+// per row keeps its NPL = ng/32 values in registers and extracts the minimum G times (each round
+// takes the smallest (value, index) pair above the previous one).  Same result as the generic
+// selection kernel at a fraction of the cost when G << ng.
+template <int NPL>
+__global__ void __launch_bounds__(256)
+topg_warp_kernel(const float* __restrict__ gmin, int64_t nq, int ng, int G, int32_t* __restrict__ groups) {
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= nq) return;
+    const float* g = gmin + row * ng;
+    const float inf = __int_as_float(0x7f800000);
+    float v[NPL];
+#pragma unroll
+    for (int i = 0; i < NPL; i++) {
+        const int j = lane + 32 * i;
+        v[i] = (j < ng) ? (g[j] + 0.0f) : inf;
+    }
+    float pv = -inf;
+    int pj = -1;
+    for (int r = 0; r < G; r++) {
+        float bv = inf;
+        int bj = 0x7fffffff;
+#pragma unroll
+        for (int i = 0; i < NPL; i++) {
+            const int j = lane + 32 * i;
+            const bool after = (v[i] > pv) || (v[i] == pv && j > pj);  // strictly after the previous pick
+            if (after && v[i] < bv && j < ng) {                          // ascending i: smallest j wins ties
+                bv = v[i];
+                bj = j;
+            }
+        }
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, bv, off);
+            const int oj = __shfl_xor_sync(0xffffffffu, bj, off);
+            if (ov < bv || (ov == bv && oj < bj)) {
+                bv = ov;
+                bj = oj;
+            }
+        }
+        if (lane == 0) groups[row * G + r] = (bj == 0x7fffffff) ? -1 : bj;
+        pv = bv;
+        pj = bj;
+        if (bj == 0x7fffffff) pv = inf;  // exhausted: every later round yields -1 as well
+    }
+}
+
 // exact canonical fp32 values of the candidates: out[row][c] = comp(value, centroid) (NONE for
 // unused slots).  ARGMIN: write the arg-min centroid to assign[row] instead.
 // rows: optional indirection (the CTA for list entry b handles row rows[b]); nrows_dev: its length.
@@ -570,8 +618,18 @@ void dfx_tc_coarse_search(dfx_index* idx, const float* d_x, int64_t nq, int npro
         const int64_t qc = std::min(QC, nq - q0);
         tc_screen(idx, d, d_x + q0 * d, qc, idx->tc_cent.p, idx->cnorm.as<float>(), nlist, idx->cfg.metric,
                   idx->tc_gmin.as<float>(), idx->tc_gmin2.as<float>(), idx->tc_gargc.as<uint8_t>(), st);
-        dfx_launch_select_cols(idx->tc_gmin.as<float>(), qc, ng, ng, G, 0, idx->tc_groups.as<int32_t>(), nullptr,
-                               nullptr, 0, st);
+        if (ng <= 512 && G <= 64) {
+            auto tk = topg_warp_kernel<16>;
+            DFX_LAUNCH(tk, (unsigned)dfx_ceil_div(qc, 8), 256, 0, st, idx->tc_gmin.as<float>(), qc, ng, G,
+                       idx->tc_groups.as<int32_t>());
+        } else if (ng <= 2048 && G <= 64) {
+            auto tk = topg_warp_kernel<64>;
+            DFX_LAUNCH(tk, (unsigned)dfx_ceil_div(qc, 8), 256, 0, st, idx->tc_gmin.as<float>(), qc, ng, G,
+                       idx->tc_groups.as<int32_t>());
+        } else {
+            dfx_launch_select_cols(idx->tc_gmin.as<float>(), qc, ng, ng, G, 0, idx->tc_groups.as<int32_t>(),
+                                   nullptr, nullptr, 0, st);
+        }
         auto kern = rerank_kernel<false>;
         DFX_LAUNCH(kern, (unsigned)qc, 128, (size_t)d * 4, st, d_x + q0 * d, d, idx->centroids.as<float>(),
                    idx->cnorm.as<float>(), nlist, idx->cfg.metric, idx->tc_groups.as<int32_t>(), G, nprobe,
