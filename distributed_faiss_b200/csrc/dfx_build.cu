@@ -527,7 +527,7 @@ __global__ void invert_ids_kernel(const int32_t* __restrict__ ids, int64_t n, in
 }
 
 // il != 0 (IVF-PQ interleaved): `inv` holds padded block positions and codes are read from
-// the interleaved blocks (byte [m*32 + (v ^ m)] of block pos/32, v = pos%32)
+// the interleaved blocks (dfx_il_byte(pos%32, m) of block pos/32)
 __global__ void reconstruct_kernel(int kind, int d, int M, int ksub, int dsub, int64_t ntotal,
                                    int64_t nlist, const int64_t* __restrict__ want,
                                    const int32_t* __restrict__ inv, const void* __restrict__ rows,
@@ -561,7 +561,7 @@ __global__ void reconstruct_kernel(int kind, int d, int M, int ksub, int dsub, i
         } else {
             int m = k / dsub;
             int code;
-            if (il) code = reinterpret_cast<const uint8_t*>(rows)[(pos >> 5) * 1024 + m * 32 + ((int)(pos & 31) ^ m)];
+            if (il) code = reinterpret_cast<const uint8_t*>(rows)[(pos >> 5) * 1024 + dfx_il_byte((int)(pos & 31), m)];
             else code = reinterpret_cast<const uint8_t*>(rows)[pos * M + m];
             v = cent[(size_t)l * d + k] + codebooks[((size_t)m * ksub + code) * dsub + (k - m * dsub)];
         }

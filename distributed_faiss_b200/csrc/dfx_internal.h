@@ -111,6 +111,17 @@ void dfx_stats_impl(dfx_index* idx, int64_t* ndis, cudaStream_t st);
 void dfx_launch_select_comp(const uint64_t* comp, int64_t nrows, int n, int64_t ld, int k, int32_t* keys,
                             cudaStream_t st);
 
+// Interleaved IVF-PQ block (M == 32): 32 vectors x 32 codes = 1 KB.  Vector v = 8u + w of the
+// block (u = group 0..3, w = 0..7) and subquantizer m = i + 8j (i = 0..7, j = 0..3) live at
+//   byte  lane*32 + r*4 + t   with lane = 8u + i,  r = w ^ i,  t = (j - u) & 3.
+// Lane (u,i) of the scanning warp owns subquantizers {i, i+8, i+16, i+24} of the 8 vectors of
+// group u: row r (one 32-bit word) holds their 4 codes in the order the lane looks them up
+// (j = (t + u) & 3, which makes the 32 simultaneous table reads hit 32 different banks).
+__host__ __device__ __forceinline__ int dfx_il_byte(int v, int m) {
+    const int u = v >> 3, w = v & 7, i = m & 7, j = m >> 3;
+    return (8 * u + i) * 32 + (w ^ i) * 4 + ((j - u) & 3);
+}
+
 // ---- dfx_scan_il.cu
 bool dfx_il_wanted(const dfx_index* idx);
 void dfx_pq_rm_to_il(dfx_index* idx, cudaStream_t st);

@@ -7,19 +7,17 @@
 //
 // Why a second layout: with one vector per lane (v1, dfx_search.cu) the 32 lanes of a warp read
 // table[m][code] for the SAME m and 32 random codes -> random shared-memory bank conflicts
-// (~3.4 wavefronts per lookup), which caps the scan at ~1/3 of the HBM roofline.  Here lane m
-// owns subquantizer m and the table is stored transposed ([code][m]), so the bank of every
-// lookup is the lane id: conflict-free by construction.  The 32 partial values of a vector then
-// sit in 32 different lanes; they are summed by a transposed butterfly (31 shuffles per 32
-// vectors) whose register indices are static because the codes are stored pre-permuted:
-//
-//   block of 32 vectors = 1 KB:  byte [m*32 + r] = code[m] of vector v = r ^ m   (r = 0..31)
-//
-// lane m loads its 32 bytes (2 x LDG.128, the warp reads the KB contiguously), looks up
-// a[r] = tableT[byte r][m], and for off = 16,8,4,2,1:  a[r] += shfl_xor(a[r + off], off) (r < off).
-// Lane m ends with the full sum for vector v = m, added in exactly the halving-tree order of
-// oracle pq_sum (s[i] += s[i+off]).  Lists are padded to whole blocks; padding carries
-// t = +inf so it can never enter a result.
+// (~3.4 wavefronts per lookup), which caps the scan at ~1/3 of the HBM roofline.  Here the table
+// is stored transposed ([code][m], bank == m) and the 32 lanes always read 32 DIFFERENT m:
+// 8 lanes share a vector, lane (u,i) owns subquantizers {i, i+8, i+16, i+24} of the 8 vectors of
+// group u and looks them up in the rotated order j = (t + u) & 3, so at every step the warp
+// touches m = i + 8*((t+u)&3): all 32 banks, conflict-free by construction.
+// The canonical halving tree of oracle pq_sum (s[x] += s[x+off], off = 16,8,4,2,1) is evaluated
+// as: in-lane (y0+y2)+(y1+y3)  [levels 16 and 8; the rotation only swaps commutative operands],
+// then a transposed butterfly over the 8 lanes of the group (levels 4,2,1: 7 shuffles per 32
+// vectors, static register indices because rows are stored pre-permuted, r = w ^ i).
+// Lane 8u+i ends with the full sum for vector 8u+i of the block (layout: dfx_il_byte()).
+// Lists are padded to whole blocks; padding carries t = +inf so it can never enter a result.
 #include "dfx_internal.h"
 #include "dfx_topk.cuh"
 
@@ -42,10 +40,10 @@ pq_rm_to_il_kernel(const int64_t* __restrict__ list_off, const int64_t* __restri
     const int64_t blk = blockIdx.x;
     const int64_t l = il_list_of_block(blk_off, nlist, blk);
     const int64_t base = list_off[l] + (blk - blk_off[l]) * 32, end = list_off[l + 1];
-    for (int b = threadIdx.x; b < 1024; b += 256) {
-        const int m = b >> 5, r = b & 31, v = r ^ m;
+    for (int e = threadIdx.x; e < 1024; e += 256) {
+        const int v = e >> 5, m = e & 31;
         const int64_t i = base + v;
-        il_codes[blk * 1024 + b] = (i < end) ? codes[i * 32 + m] : (uint8_t)0;
+        il_codes[blk * 1024 + dfx_il_byte(v, m)] = (i < end) ? codes[i * 32 + m] : (uint8_t)0;
     }
     if (threadIdx.x < 32) {
         const int64_t i = base + threadIdx.x;
@@ -62,10 +60,10 @@ pq_il_to_rm_kernel(const int64_t* __restrict__ list_off, const int64_t* __restri
     const int64_t blk = blockIdx.x;
     const int64_t l = il_list_of_block(blk_off, nlist, blk);
     const int64_t base = list_off[l] + (blk - blk_off[l]) * 32, end = list_off[l + 1];
-    for (int b = threadIdx.x; b < 1024; b += 256) {
-        const int m = b >> 5, r = b & 31, v = r ^ m;
+    for (int e = threadIdx.x; e < 1024; e += 256) {
+        const int v = e >> 5, m = e & 31;
         const int64_t i = base + v;
-        if (i < end) codes[i * 32 + m] = il_codes[blk * 1024 + b];
+        if (i < end) codes[i * 32 + m] = il_codes[blk * 1024 + dfx_il_byte(v, m)];
     }
     if (threadIdx.x < 32) {
         const int64_t i = base + threadIdx.x;
@@ -151,7 +149,13 @@ scan_pq_il_kernel(const float* __restrict__ lutT, const float* __restrict__ dis0
     WarpTopK wt;
     wt.init(s_buf + (size_t)warp * cap, cap, k);
     __syncthreads();
-    const char* lut_lane = reinterpret_cast<const char*>(s_lut) + lane * 4;  // + code*128 per lookup
+    // byte offsets (inside a 128-byte table row) of the 4 subquantizers this lane looks up, in
+    // lookup order: m_t = i + 8*((t+u)&3)
+    const uint32_t li = lane & 7, lu = lane >> 3;
+    const uint32_t lut_base = (uint32_t)__cvta_generic_to_shared(s_lut);
+    uint32_t moff[4];
+#pragma unroll
+    for (int t = 0; t < 4; t++) moff[t] = lut_base + (li + 8u * ((t + lu) & 3u)) * 4u;
 
     const int p_end = min(nprobe, (g + 1) * G);
     for (int p = g * G; p < p_end; p++) {
@@ -173,14 +177,21 @@ scan_pq_il_kernel(const float* __restrict__ lutT, const float* __restrict__ dis0
                 c0 = __ldg(il_codes + bn * 64 + lane * 2);
                 c1 = __ldg(il_codes + bn * 64 + lane * 2 + 1);
             }
-            float a[32];
+            float a[8];
 #pragma unroll
-            for (int r = 0; r < 32; r++) {
-                const uint32_t code = (w[r >> 2] >> (8 * (r & 3))) & 255u;
-                a[r] = *reinterpret_cast<const float*>(lut_lane + code * 128);
+            for (int r = 0; r < 8; r++) {
+                float y[4];
+#pragma unroll
+                for (int t = 0; t < 4; t++) {
+                    // (code << 7) + per-lane column offset; table rows are 128 bytes
+                    const uint32_t sh = (t == 0) ? (w[r] << 7) : (w[r] >> (8 * t - 7));
+                    const uint32_t addr = (sh & 0x7f80u) + moff[t];
+                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(y[t]) : "r"(addr));
+                }
+                a[r] = (y[0] + y[2]) + (y[1] + y[3]);  // tree levels 16 and 8
             }
 #pragma unroll
-            for (int off = 16; off >= 1; off >>= 1) {
+            for (int off = 4; off >= 1; off >>= 1) {  // tree levels 4, 2, 1 across the 8 lanes
 #pragma unroll
                 for (int r = 0; r < off; r++) a[r] = a[r] + __shfl_xor_sync(0xffffffffu, a[r + off], off);
             }
