@@ -128,6 +128,20 @@ void dfx_pq_il_to_rm(dfx_index* idx, cudaStream_t st) {
 }
 
 // ------------------------------------------------------------------ the scan
+// streaming global loads: read once, do not allocate in L1
+__device__ __forceinline__ uint4 ld_stream(const uint4* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+__device__ __forceinline__ float ld_stream_f(const float* p) {
+    float r;
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));
+    return r;
+}
+
 // lutT: [nq][256][32] (transposed table, written by pq_prep_kernel)
 constexpr int IL_THREADS = 256;  // 8 warps: 4 CTAs/SM = 32 warps/SM (the 64-register limit)
 __global__ void __launch_bounds__(IL_THREADS)
@@ -163,19 +177,32 @@ scan_pq_il_kernel(const float* __restrict__ lutT, const float* __restrict__ dis0
         if (l < 0) continue;
         const float d0 = dis0[q * nprobe + p];
         const int64_t bend = blk_off[l + 1];
+        constexpr int S = IL_THREADS / 32;  // block stride of one warp
         int64_t b = blk_off[l] + warp;
-        uint4 c0, c1;
+        // two blocks of look-ahead per warp (codes + t), streaming loads: ~2.3 KB in flight per warp
+        uint4 n0a, n0b, n1a, n1b;
+        float nt0 = 0.f, nt1 = 0.f;
         if (b < bend) {
-            c0 = __ldg(il_codes + b * 64 + lane * 2);
-            c1 = __ldg(il_codes + b * 64 + lane * 2 + 1);
+            n0a = ld_stream(il_codes + b * 64 + lane * 2);
+            n0b = ld_stream(il_codes + b * 64 + lane * 2 + 1);
+            nt0 = ld_stream_f(il_tvals + b * 32 + lane);
+        }
+        if (b + S < bend) {
+            n1a = ld_stream(il_codes + (b + S) * 64 + lane * 2);
+            n1b = ld_stream(il_codes + (b + S) * 64 + lane * 2 + 1);
+            nt1 = ld_stream_f(il_tvals + (b + S) * 32 + lane);
         }
         while (b < bend) {
-            const uint32_t w[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
-            const float tv = __ldg(il_tvals + b * 32 + lane);
-            const int64_t bn = b + IL_THREADS / 32;
-            if (bn < bend) {  // prefetch the next block of this warp
-                c0 = __ldg(il_codes + bn * 64 + lane * 2);
-                c1 = __ldg(il_codes + bn * 64 + lane * 2 + 1);
+            const uint32_t w[8] = {n0a.x, n0a.y, n0a.z, n0a.w, n0b.x, n0b.y, n0b.z, n0b.w};
+            const float tv = nt0;
+            n0a = n1a;
+            n0b = n1b;
+            nt0 = nt1;
+            const int64_t bn = b + S;
+            if (b + 2 * S < bend) {
+                n1a = ld_stream(il_codes + (b + 2 * S) * 64 + lane * 2);
+                n1b = ld_stream(il_codes + (b + 2 * S) * 64 + lane * 2 + 1);
+                nt1 = ld_stream_f(il_tvals + (b + 2 * S) * 32 + lane);
             }
             float a[8];
 #pragma unroll

@@ -204,18 +204,26 @@ pq_prep_kernel(const float* __restrict__ Q, int d, int M, int ksub, int dsub,
     if (lut) {
         const int tot = M * ksub;
         for (int idx = threadIdx.x; idx < tot; idx += blockDim.x) {
-            int m = idx / ksub;
+            const int m = (ksub == 256) ? (idx >> 8) : (idx / ksub);
             const float* p = codebooks + (size_t)idx * dsub;
             const float* qm = s_q + m * dsub;
             float acc = 0.f;
-            for (int t = 0; t < dsub; t++) acc = __fmaf_rn(qm[t], p[t], acc);
+            if (dsub == 4) {  // same seq-k order, one 16-byte load
+                const float4 pv = __ldg(reinterpret_cast<const float4*>(p));
+                acc = __fmaf_rn(qm[0], pv.x, acc);
+                acc = __fmaf_rn(qm[1], pv.y, acc);
+                acc = __fmaf_rn(qm[2], pv.z, acc);
+                acc = __fmaf_rn(qm[3], pv.w, acc);
+            } else {
+                for (int t = 0; t < dsub; t++) acc = __fmaf_rn(qm[t], p[t], acc);
+            }
             if (transposed) s_t[m * (ksub + 1) + (idx - m * ksub)] = -2.f * acc;
             else lut[q * tot + idx] = -2.f * acc;
         }
-        if (transposed) {
+        if (transposed) {  // M == 32 here
             __syncthreads();
             for (int o = threadIdx.x; o < tot; o += blockDim.x) {
-                const int j = o / M, m = o - j * M;
+                const int j = o >> 5, m = o & 31;
                 lut[q * tot + o] = s_t[m * (ksub + 1) + j];
             }
         }

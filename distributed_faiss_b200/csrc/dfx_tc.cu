@@ -18,8 +18,8 @@
 //      (seq-k FMA, identical to oracle/dfx_oracle.c) and the final top-nprobe / argmin is
 //      taken on those exact values -> the probe lists are bit-identical to the oracle's.
 //
-// One CTA = 6 warps: warp 0 TMA producer, warp 1 TMEM allocator + single-thread MMA issuer,
-// warps 2..5 epilogue (one TMEM lane == one query row per thread).  A (query planes) stays
+// One CTA = 10 warps: warp 0 TMA producer, warp 1 TMEM allocator + single-thread MMA issuer,
+// warps 2..9 epilogue (one TMEM lane == one query row per thread, two warps per lane quadrant).  A (query planes) stays
 // resident in shared memory, B (centroid planes) streams through a ring of 16 KB stages, two
 // TMEM accumulator buffers overlap the epilogue of tile i with the MMAs of tile i+1.
 #include "dfx_internal.h"
@@ -120,7 +120,7 @@ constexpr int TILE = 128;           // rows of A and of B per tile
 constexpr int KATOM = 64;           // bf16 elements per 128-byte swizzle row
 constexpr int ATOM_BYTES = TILE * KATOM * 2;  // 16 KB
 constexpr int NSTAGE = 8;
-constexpr int THREADS = 192;
+constexpr int THREADS = 320;        // TMA warp + MMA warp + 8 epilogue warps
 constexpr int TMEM_COLS = 256;      // two 128-column accumulator buffers
 struct Smem {
     // offsets inside the 1024-aligned dynamic shared memory block
@@ -170,7 +170,7 @@ tc_coarse_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         mbar_init(a_full, 1);
         for (int b = 0; b < 2; b++) {
             mbar_init(&t_full[b], 1);
-            mbar_init(&t_empty[b], 4);
+            mbar_init(&t_empty[b], 8);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -245,53 +245,65 @@ tc_coarse_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             }
         }
     } else {
-        // ===================== epilogue: TMEM -> group minima =====================
+        // ===================== epilogue: TMEM -> per-group (min, runner-up, argmin) =============
+        // 8 warps: two per TMEM lane quadrant (a warp may only touch lanes 32*(warp%4)..+31);
+        // the pair splits the tile's four 32-column groups between them.
         const int quad = warp & 3;             // TMEM lane quadrant this warp may access
+        const int half = (warp - 2) >> 2;      // 0: groups 0,1   1: groups 2,3
         const int row = quad * 32 + lane;      // query row inside the tile == TMEM lane
         const int64_t grow = (int64_t)qt * TILE + row;
-        const int et = threadIdx.x - 64;       // 0..127
+        const int et = threadIdx.x - 64;       // 0..255
+        const float inf = __int_as_float(0x7f800000);
         for (int t = 0; t < ntiles; t++) {
             const int buf = t & 1;
             const int col0 = (ct0 + t) * TILE;
-            {
+            if (et < TILE) {
                 const int c = col0 + et;
                 float cn = 0.f;
                 if (metric == DFX_METRIC_L2 && c < nlist) cn = cnorm[c];
-                s_cn[buf * TILE + et] = (c < nlist) ? cn : __int_as_float(0x7f800000);
+                s_cn[buf * TILE + et] = (c < nlist) ? cn : inf;
             }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            asm volatile("bar.sync 1, 256;" ::: "memory");
             mbar_wait(&t_full[buf], (t >> 1) & 1);
             tc_fence_after();
-            float gm[4], gm2[4];
+            float gm[2], gm2[2];
             uint32_t ga = 0;
 #pragma unroll
-            for (int ch = 0; ch < 4; ch++) {
+            for (int cc = 0; cc < 2; cc++) {
+                const int ch = half * 2 + cc;
                 uint32_t r[32];
                 tc_ld32(tmem_base + buf * TILE + ch * 32 + ((uint32_t)(quad * 32) << 16), r);
-                float m1 = __int_as_float(0x7f800000), m2 = m1;
-                uint32_t a1 = 0;
+                // two independent (min, runner-up, argmin) chains over even / odd columns
+                float m1[2] = {inf, inf}, m2[2] = {inf, inf};
+                uint32_t a1[2] = {0, 0};
 #pragma unroll
                 for (int j = 0; j < 32; j++) {
                     const float ip = __uint_as_float(r[j]);
                     const float cn = s_cn[buf * TILE + ch * 32 + j];
                     const float v = (metric == DFX_METRIC_IP) ? (cn - ip) : fmaf(-2.f, ip, cn);
-                    const bool lt = v < m1;
-                    m2 = lt ? m1 : fminf(m2, v);
-                    a1 = lt ? (uint32_t)j : a1;
-                    m1 = lt ? v : m1;
+                    const int e = j & 1;
+                    const bool lt = v < m1[e];
+                    m2[e] = lt ? m1[e] : fminf(m2[e], v);
+                    a1[e] = lt ? (uint32_t)j : a1[e];
+                    m1[e] = lt ? v : m1[e];
                 }
-                gm[ch] = m1;
-                gm2[ch] = m2;
-                ga |= a1 << (8 * ch);
+                // merge: ties keep the smaller column (chain 0 holds the even, i.e. smaller-or-equal,
+                // column only when its value is <=)
+                const bool take1 = (m1[1] < m1[0]) || (m1[1] == m1[0] && a1[1] < a1[0]);
+                const float lo = take1 ? m1[1] : m1[0];
+                const float hi = take1 ? m1[0] : m1[1];
+                gm[cc] = lo;
+                gm2[cc] = fminf(hi, fminf(m2[0], m2[1]));
+                ga |= (take1 ? a1[1] : a1[0]) << (8 * cc);
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&t_empty[buf]);
             if (grow < nq) {
-                const int64_t o = grow * ng + (col0 >> 5);
-                *reinterpret_cast<float4*>(gmin + o) = make_float4(gm[0], gm[1], gm[2], gm[3]);
-                *reinterpret_cast<float4*>(gmin2 + o) = make_float4(gm2[0], gm2[1], gm2[2], gm2[3]);
-                *reinterpret_cast<uint32_t*>(gargc + o) = ga;
+                const int64_t o = grow * ng + (col0 >> 5) + half * 2;
+                *reinterpret_cast<float2*>(gmin + o) = make_float2(gm[0], gm[1]);
+                *reinterpret_cast<float2*>(gmin2 + o) = make_float2(gm2[0], gm2[1]);
+                *reinterpret_cast<uint16_t*>(gargc + o) = (uint16_t)ga;
             }
         }
     }
@@ -404,25 +416,32 @@ topg_warp_kernel(const float* __restrict__ gmin, int64_t nq, int ng, int G, int3
     }
 }
 
-// exact canonical fp32 values of the candidates: out[row][c] = comp(value, centroid) (NONE for
-// unused slots).  ARGMIN: write the arg-min centroid to assign[row] instead.
+// exact canonical fp32 values of the candidates.
+//   MODE 0: out[row][c] = comp(value, centroid) for every candidate slot (NONE for unused slots)
+//   MODE 1: write the arg-min centroid to assign[row]
+//   MODE 2: select the nprobe smallest in shared memory and write keys[row][0..nprobe) (sorted)
 // rows: optional indirection (the CTA for list entry b handles row rows[b]); nrows_dev: its length.
-template <bool ARGMIN>
+template <int MODE>
 __global__ void __launch_bounds__(128)
 rerank_kernel(const float* __restrict__ Q, int d, const float* __restrict__ cent, const float* __restrict__ cnorm,
               int64_t nlist, int metric, const int32_t* __restrict__ groups, int G, int nprobe,
               const float* __restrict__ gmin, const float* __restrict__ gmin2, const uint8_t* __restrict__ gargc,
               int ng, float cmax2, uint64_t* __restrict__ out, int32_t* __restrict__ assign,
-              const int32_t* __restrict__ rows, const int32_t* __restrict__ nrows_dev, int64_t nrows) {
-    extern __shared__ float s_q[];
+              const int32_t* __restrict__ rows, const int32_t* __restrict__ nrows_dev, int64_t nrows,
+              int32_t* __restrict__ keys) {
+    extern __shared__ __align__(16) unsigned char rr_smem[];
+    float* s_q = reinterpret_cast<float*>(rr_smem);
+    uint64_t* s_c = reinterpret_cast<uint64_t*>(rr_smem + ((size_t)d * 4 + 15) / 16 * 16);  // MODE 2
     __shared__ unsigned long long s_best[4];
     __shared__ float s_thr;
+    __shared__ int s_cnt;
     const int ncand = G * 32;
     const int64_t limit = nrows_dev ? (int64_t)*nrows_dev : nrows;
     for (int64_t b = blockIdx.x; b < limit; b += gridDim.x) {
         const int64_t row = rows ? rows[b] : b;
         __syncthreads();
         for (int i = threadIdx.x; i < d; i += 128) s_q[i] = Q[row * d + i];
+        if (threadIdx.x == 0) s_cnt = 0;
         __syncthreads();
         if (threadIdx.x == 0) {
             float qn2 = 0.f;
@@ -456,10 +475,11 @@ rerank_kernel(const float* __restrict__ Q, int d, const float* __restrict__ cent
                     comp = dfx_comp(v, (uint32_t)col);
                 }
             }
-            if (ARGMIN) best = comp < best ? comp : best;
-            else out[row * ncand + c] = comp;
+            if (MODE == 1) best = comp < best ? comp : best;
+            else if (MODE == 0) out[row * ncand + c] = comp;
+            else if (comp != DFX_COMP_NONE) s_c[atomicAdd(&s_cnt, 1)] = comp;
         }
-        if (ARGMIN) {
+        if (MODE == 1) {
 #pragma unroll
             for (int off = 16; off >= 1; off >>= 1) {
                 unsigned long long o = __shfl_xor_sync(0xffffffffu, best, off);
@@ -470,6 +490,18 @@ rerank_kernel(const float* __restrict__ Q, int d, const float* __restrict__ cent
             if (threadIdx.x == 0) {
                 for (int w = 1; w < 4; w++) best = s_best[w] < best ? s_best[w] : best;
                 assign[row] = (best == DFX_COMP_NONE) ? -1 : (int32_t)(uint32_t)best;
+            }
+        }
+        if (MODE == 2) {
+            __syncthreads();
+            const int cnt = s_cnt;
+            int P = 32;
+            while (P < cnt) P <<= 1;
+            for (int e = cnt + threadIdx.x; e < P; e += 128) s_c[e] = DFX_COMP_NONE;
+            dfx_block_bitonic_sort<128>(s_c, P);
+            for (int j = threadIdx.x; j < nprobe; j += 128) {
+                const uint64_t c = (j < P) ? s_c[j] : DFX_COMP_NONE;
+                keys[row * nprobe + j] = (c == DFX_COMP_NONE) ? -1 : (int32_t)(uint32_t)c;
             }
         }
     }
@@ -613,7 +645,6 @@ void dfx_tc_coarse_search(dfx_index* idx, const float* d_x, int64_t nq, int npro
     idx->tc_gmin2.reserve((size_t)qmax * ng * 4);
     idx->tc_gargc.reserve((size_t)qmax * ng);
     idx->tc_groups.reserve((size_t)qmax * G * 4);
-    idx->tc_cand.reserve((size_t)qmax * G * 32 * 8);
     for (int64_t q0 = 0; q0 < nq; q0 += QC) {
         const int64_t qc = std::min(QC, nq - q0);
         tc_screen(idx, d, d_x + q0 * d, qc, idx->tc_cent.p, idx->cnorm.as<float>(), nlist, idx->cfg.metric,
@@ -630,14 +661,26 @@ void dfx_tc_coarse_search(dfx_index* idx, const float* d_x, int64_t nq, int npro
             dfx_launch_select_cols(idx->tc_gmin.as<float>(), qc, ng, ng, G, 0, idx->tc_groups.as<int32_t>(),
                                    nullptr, nullptr, 0, st);
         }
-        auto kern = rerank_kernel<false>;
-        DFX_LAUNCH(kern, (unsigned)qc, 128, (size_t)d * 4, st, d_x + q0 * d, d, idx->centroids.as<float>(),
-                   idx->cnorm.as<float>(), nlist, idx->cfg.metric, idx->tc_groups.as<int32_t>(), G, nprobe,
-                   idx->tc_gmin.as<float>(), idx->tc_gmin2.as<float>(), idx->tc_gargc.as<uint8_t>(), ng,
-                   idx->tc_cmax2, idx->tc_cand.as<uint64_t>(), (int32_t*)nullptr, (const int32_t*)nullptr,
-                   (const int32_t*)nullptr, qc);
-        dfx_launch_select_comp(idx->tc_cand.as<uint64_t>(), qc, G * 32, (int64_t)G * 32, nprobe, keys + q0 * nprobe,
-                               st);
+        const int P_cand = dfx_next_pow2(G * 32 < 32 ? 32 : G * 32);
+        if (P_cand <= 4096) {  // fused: candidates never leave the SM
+            auto kern = rerank_kernel<2>;
+            const size_t smem = ((size_t)d * 4 + 15) / 16 * 16 + (size_t)P_cand * 8;
+            DFX_LAUNCH(kern, (unsigned)qc, 128, smem, st, d_x + q0 * d, d, idx->centroids.as<float>(),
+                       idx->cnorm.as<float>(), nlist, idx->cfg.metric, idx->tc_groups.as<int32_t>(), G, nprobe,
+                       idx->tc_gmin.as<float>(), idx->tc_gmin2.as<float>(), idx->tc_gargc.as<uint8_t>(), ng,
+                       idx->tc_cmax2, (uint64_t*)nullptr, (int32_t*)nullptr, (const int32_t*)nullptr,
+                       (const int32_t*)nullptr, qc, keys + q0 * nprobe);
+        } else {
+            idx->tc_cand.reserve((size_t)qmax * G * 32 * 8);
+            auto kern = rerank_kernel<0>;
+            DFX_LAUNCH(kern, (unsigned)qc, 128, (size_t)d * 4, st, d_x + q0 * d, d, idx->centroids.as<float>(),
+                       idx->cnorm.as<float>(), nlist, idx->cfg.metric, idx->tc_groups.as<int32_t>(), G, nprobe,
+                       idx->tc_gmin.as<float>(), idx->tc_gmin2.as<float>(), idx->tc_gargc.as<uint8_t>(), ng,
+                       idx->tc_cmax2, idx->tc_cand.as<uint64_t>(), (int32_t*)nullptr, (const int32_t*)nullptr,
+                       (const int32_t*)nullptr, qc, (int32_t*)nullptr);
+            dfx_launch_select_comp(idx->tc_cand.as<uint64_t>(), qc, G * 32, (int64_t)G * 32, nprobe,
+                                   keys + q0 * nprobe, st);
+        }
     }
 }
 
@@ -677,11 +720,11 @@ void dfx_tc_assign(dfx_index* idx, int d, const float* d_cent, const float* d_cn
         DFX_LAUNCH(assign_resolve_kernel, (unsigned)dfx_ceil_div(rc, 256), 256, 0, st, idx->tc_qn.as<float>(),
                    idx->tc_groups.as<int32_t>(), idx->tc_gmin.as<float>(), idx->tc_gmin2.as<float>(),
                    idx->tc_gargc.as<uint8_t>(), ng, cmax2, rc, d_assign + r0, amb_rows, amb_count);
-        auto kern = rerank_kernel<true>;
+        auto kern = rerank_kernel<1>;
         const unsigned grid = (unsigned)std::min<int64_t>(rc, 148 * 16);
         DFX_LAUNCH(kern, grid, 128, (size_t)d * 4, st, xr, d, d_cent, d_cnorm, nlist, metric,
                    idx->tc_groups.as<int32_t>(), G, 1, idx->tc_gmin.as<float>(), idx->tc_gmin2.as<float>(),
                    idx->tc_gargc.as<uint8_t>(), ng, cmax2, (uint64_t*)nullptr, d_assign + r0,
-                   (const int32_t*)amb_rows, (const int32_t*)amb_count, rc);
+                   (const int32_t*)amb_rows, (const int32_t*)amb_count, rc, (int32_t*)nullptr);
     }
 }
