@@ -18,8 +18,8 @@
 //      (seq-k FMA, identical to oracle/dfx_oracle.c) and the final top-nprobe / argmin is
 //      taken on those exact values -> the probe lists are bit-identical to the oracle's.
 //
-// One CTA = 10 warps: warp 0 TMA producer, warp 1 TMEM allocator + single-thread MMA issuer,
-// warps 2..9 epilogue (one TMEM lane == one query row per thread, two warps per lane quadrant).  A (query planes) stays
+// One CTA = 6 warps: warp 0 TMA producer, warp 1 TMEM allocator + single-thread MMA issuer,
+// warps 2..5 epilogue (one TMEM lane == one query row per thread).  A (query planes) stays
 // resident in shared memory, B (centroid planes) streams through a ring of 16 KB stages, two
 // TMEM accumulator buffers overlap the epilogue of tile i with the MMAs of tile i+1.
 #include "dfx_internal.h"
@@ -120,7 +120,7 @@ constexpr int TILE = 128;           // rows of A and of B per tile
 constexpr int KATOM = 64;           // bf16 elements per 128-byte swizzle row
 constexpr int ATOM_BYTES = TILE * KATOM * 2;  // 16 KB
 constexpr int NSTAGE = 8;
-constexpr int THREADS = 320;        // TMA warp + MMA warp + 8 epilogue warps
+constexpr int THREADS = 192;        // TMA warp + MMA warp + 4 epilogue warps
 constexpr int TMEM_COLS = 256;      // two 128-column accumulator buffers
 struct Smem {
     // offsets inside the 1024-aligned dynamic shared memory block
@@ -134,7 +134,7 @@ struct Smem {
 // tmQ: bf16 [2*nq_pad, d]  (rows [0,nq_pad) = hi plane, [nq_pad, 2 nq_pad) = lo plane)
 // tmC: bf16 [2*nl_pad, d]
 // gmin: float [nq][ng], ng = nl_pad/32
-template <int KATOMS>
+template <int KATOMS, int METRIC>
 __global__ void __launch_bounds__(tc::THREADS, 1)
 tc_coarse_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmC, int nq,
                  int nq_pad, int nlist, int nl_pad, const float* __restrict__ cnorm, int metric, int ctiles_per_cta,
@@ -170,7 +170,7 @@ tc_coarse_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         mbar_init(a_full, 1);
         for (int b = 0; b < 2; b++) {
             mbar_init(&t_full[b], 1);
-            mbar_init(&t_empty[b], 8);
+            mbar_init(&t_empty[b], 4);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -246,64 +246,55 @@ tc_coarse_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         }
     } else {
         // ===================== epilogue: TMEM -> per-group (min, runner-up, argmin) =============
-        // 8 warps: two per TMEM lane quadrant (a warp may only touch lanes 32*(warp%4)..+31);
-        // the pair splits the tile's four 32-column groups between them.
+        // The epilogue is bound by the half-rate ALU pipe, so it is kept to 3 FMNMX + 1 LOP3 per
+        // element: the column index (0..31) replaces the 5 low mantissa bits of the screening
+        // value (a 2^-18 relative perturbation, far below the screening tolerance), which makes
+        // the arg-min fall out of the minimum itself; the runner-up is min(m2, max(m1, v)).
         const int quad = warp & 3;             // TMEM lane quadrant this warp may access
-        const int half = (warp - 2) >> 2;      // 0: groups 0,1   1: groups 2,3
         const int row = quad * 32 + lane;      // query row inside the tile == TMEM lane
         const int64_t grow = (int64_t)qt * TILE + row;
-        const int et = threadIdx.x - 64;       // 0..255
-        const float inf = __int_as_float(0x7f800000);
+        const int et = threadIdx.x - 64;       // 0..127
+        const float big = 3.0e38f;             // out-of-range columns: finite, never selected
         for (int t = 0; t < ntiles; t++) {
             const int buf = t & 1;
             const int col0 = (ct0 + t) * TILE;
-            if (et < TILE) {
+            {
                 const int c = col0 + et;
                 float cn = 0.f;
-                if (metric == DFX_METRIC_L2 && c < nlist) cn = cnorm[c];
-                s_cn[buf * TILE + et] = (c < nlist) ? cn : inf;
+                if (METRIC == DFX_METRIC_L2 && c < nlist) cn = cnorm[c];
+                s_cn[buf * TILE + et] = (c < nlist) ? cn : big;
             }
-            asm volatile("bar.sync 1, 256;" ::: "memory");
+            asm volatile("bar.sync 1, 128;" ::: "memory");
             mbar_wait(&t_full[buf], (t >> 1) & 1);
             tc_fence_after();
-            float gm[2], gm2[2];
+            float gm[4], gm2[4];
             uint32_t ga = 0;
 #pragma unroll
-            for (int cc = 0; cc < 2; cc++) {
-                const int ch = half * 2 + cc;
+            for (int ch = 0; ch < 4; ch++) {
                 uint32_t r[32];
                 tc_ld32(tmem_base + buf * TILE + ch * 32 + ((uint32_t)(quad * 32) << 16), r);
-                // two independent (min, runner-up, argmin) chains over even / odd columns
-                float m1[2] = {inf, inf}, m2[2] = {inf, inf};
-                uint32_t a1[2] = {0, 0};
+                float m1 = big, m2 = big;
 #pragma unroll
                 for (int j = 0; j < 32; j++) {
                     const float ip = __uint_as_float(r[j]);
                     const float cn = s_cn[buf * TILE + ch * 32 + j];
-                    const float v = (metric == DFX_METRIC_IP) ? (cn - ip) : fmaf(-2.f, ip, cn);
-                    const int e = j & 1;
-                    const bool lt = v < m1[e];
-                    m2[e] = lt ? m1[e] : fminf(m2[e], v);
-                    a1[e] = lt ? (uint32_t)j : a1[e];
-                    m1[e] = lt ? v : m1[e];
+                    const float v = (METRIC == DFX_METRIC_IP) ? (cn - ip) : fmaf(-2.f, ip, cn);
+                    const float vj = __uint_as_float((__float_as_uint(v) & ~31u) | (uint32_t)j);
+                    m2 = fminf(m2, fmaxf(m1, vj));
+                    m1 = fminf(m1, vj);
                 }
-                // merge: ties keep the smaller column (chain 0 holds the even, i.e. smaller-or-equal,
-                // column only when its value is <=)
-                const bool take1 = (m1[1] < m1[0]) || (m1[1] == m1[0] && a1[1] < a1[0]);
-                const float lo = take1 ? m1[1] : m1[0];
-                const float hi = take1 ? m1[0] : m1[1];
-                gm[cc] = lo;
-                gm2[cc] = fminf(hi, fminf(m2[0], m2[1]));
-                ga |= (take1 ? a1[1] : a1[0]) << (8 * cc);
+                gm[ch] = m1;
+                gm2[ch] = m2;
+                ga |= (__float_as_uint(m1) & 31u) << (8 * ch);
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&t_empty[buf]);
             if (grow < nq) {
-                const int64_t o = grow * ng + (col0 >> 5) + half * 2;
-                *reinterpret_cast<float2*>(gmin + o) = make_float2(gm[0], gm[1]);
-                *reinterpret_cast<float2*>(gmin2 + o) = make_float2(gm2[0], gm2[1]);
-                *reinterpret_cast<uint16_t*>(gargc + o) = (uint16_t)ga;
+                const int64_t o = grow * ng + (col0 >> 5);
+                *reinterpret_cast<float4*>(gmin + o) = make_float4(gm[0], gm[1], gm[2], gm[3]);
+                *reinterpret_cast<float4*>(gmin2 + o) = make_float4(gm2[0], gm2[1], gm2[2], gm2[3]);
+                *reinterpret_cast<uint32_t*>(gargc + o) = ga;
             }
         }
     }
@@ -365,7 +356,9 @@ __global__ void topg_small_kernel(const float* __restrict__ gmin, int64_t nq, in
 // approx(c) >= gmin2(group).  So a group is expanded to all 32 columns only if
 // gmin2 <= t + tol, otherwise its arg-min column is the only candidate.
 __device__ __forceinline__ float screen_tol(float qn2, float cmax2) {
-    return 1e-4f * sqrtf(qn2 * cmax2) + 1e-30f;
+    // bf16-split error ~1e-5 |q||c|, plus the 2^-18 |v| perturbation of the packed column index
+    // (|v| <= |c|^2 + 2|q||c|); both with a wide margin
+    return 1e-4f * (sqrtf(qn2 * cmax2) + cmax2) + 1e-30f;
 }
 
 // The G smallest group minima of a row, ascending by (value, group), for any G <= ng: one warp
@@ -618,17 +611,18 @@ static void tc_screen(dfx_index* idx, int d, const float* d_x, int64_t nq, const
     const size_t smem = (size_t)Smem::total(katoms) + 1024;
     dim3 grid((unsigned)csplit, (unsigned)qtiles);
     DFX_REQUIRE(qtiles <= 65535, "too many query tiles in one screening launch");
-    if (katoms == 2) {
-        auto kern = tc_coarse_kernel<2>;
-        DFX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        DFX_LAUNCH(kern, grid, THREADS, smem, st, tmQ, tmC, (int)nq, (int)nq_pad, (int)nlist, (int)nl_pad, cnorm,
-                   metric, per, gmin, gmin2, gargc, ng);
-    } else {
-        auto kern = tc_coarse_kernel<1>;
-        DFX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        DFX_LAUNCH(kern, grid, THREADS, smem, st, tmQ, tmC, (int)nq, (int)nq_pad, (int)nlist, (int)nl_pad, cnorm,
-                   metric, per, gmin, gmin2, gargc, ng);
-    }
+#define DFX_TC_LAUNCH(KA, MT)                                                                            \
+    do {                                                                                                 \
+        auto kern = tc_coarse_kernel<KA, MT>;                                                            \
+        DFX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
+        DFX_LAUNCH(kern, grid, THREADS, smem, st, tmQ, tmC, (int)nq, (int)nq_pad, (int)nlist, (int)nl_pad, \
+                   cnorm, metric, per, gmin, gmin2, gargc, ng);                                          \
+    } while (0)
+    if (katoms == 2 && metric == DFX_METRIC_L2) DFX_TC_LAUNCH(2, DFX_METRIC_L2);
+    else if (katoms == 2) DFX_TC_LAUNCH(2, DFX_METRIC_IP);
+    else if (metric == DFX_METRIC_L2) DFX_TC_LAUNCH(1, DFX_METRIC_L2);
+    else DFX_TC_LAUNCH(1, DFX_METRIC_IP);
+#undef DFX_TC_LAUNCH
 }
 
 // top-nprobe lists per query -> keys int32 [nq, nprobe] (exactly the oracle's coarse result)
