@@ -142,6 +142,12 @@ __device__ __forceinline__ float ld_stream_f(const float* p) {
     return r;
 }
 
+__device__ __forceinline__ uint32_t ld_stream_u(const int32_t* p) {
+    uint32_t r;
+    asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r) : "l"(p));
+    return r;
+}
+
 // lutT: [nq][256][32] (transposed table, written by pq_prep_kernel)
 constexpr int IL_THREADS = 256;  // 8 warps: 4 CTAs/SM = 32 warps/SM (the 64-register limit)
 __global__ void __launch_bounds__(IL_THREADS)
@@ -180,29 +186,37 @@ scan_pq_il_kernel(const float* __restrict__ lutT, const float* __restrict__ dis0
         constexpr int S = IL_THREADS / 32;  // block stride of one warp
         int64_t b = blk_off[l] + warp;
         // two blocks of look-ahead per warp (codes + t), streaming loads: ~2.3 KB in flight per warp
+        // (the ids ride along: fetching an id only when a candidate is admitted would put a full
+        // DRAM latency on the critical path of every admission)
         uint4 n0a, n0b, n1a, n1b;
         float nt0 = 0.f, nt1 = 0.f;
+        uint32_t ni0 = DFX_SEC_NONE, ni1 = DFX_SEC_NONE;
         if (b < bend) {
             n0a = ld_stream(il_codes + b * 64 + lane * 2);
             n0b = ld_stream(il_codes + b * 64 + lane * 2 + 1);
             nt0 = ld_stream_f(il_tvals + b * 32 + lane);
+            ni0 = ld_stream_u(il_ids + b * 32 + lane);
         }
         if (b + S < bend) {
             n1a = ld_stream(il_codes + (b + S) * 64 + lane * 2);
             n1b = ld_stream(il_codes + (b + S) * 64 + lane * 2 + 1);
             nt1 = ld_stream_f(il_tvals + (b + S) * 32 + lane);
+            ni1 = ld_stream_u(il_ids + (b + S) * 32 + lane);
         }
         while (b < bend) {
             const uint32_t w[8] = {n0a.x, n0a.y, n0a.z, n0a.w, n0b.x, n0b.y, n0b.z, n0b.w};
             const float tv = nt0;
+            const uint32_t my_id = ni0;
             n0a = n1a;
             n0b = n1b;
             nt0 = nt1;
+            ni0 = ni1;
             const int64_t bn = b + S;
             if (b + 2 * S < bend) {
                 n1a = ld_stream(il_codes + (b + 2 * S) * 64 + lane * 2);
                 n1b = ld_stream(il_codes + (b + 2 * S) * 64 + lane * 2 + 1);
                 nt1 = ld_stream_f(il_tvals + (b + 2 * S) * 32 + lane);
+                ni1 = ld_stream_u(il_ids + (b + 2 * S) * 32 + lane);
             }
             float a[8];
 #pragma unroll
@@ -224,7 +238,7 @@ scan_pq_il_kernel(const float* __restrict__ lutT, const float* __restrict__ dis0
             }
             const float v = d0 + (tv + a[0]);  // vector `lane` of this block; padding has tv = +inf
             uint32_t sec = 0;
-            const bool want = wt.admits(v, [&] { return (uint32_t)__ldg(il_ids + b * 32 + lane); }, sec);
+            const bool want = wt.admits(v, [&] { return my_id; }, sec);
             wt.push_lanes(want, v, sec);
             b = bn;
         }

@@ -289,7 +289,9 @@ scan_pq_kernel(const float* __restrict__ lut, const float* __restrict__ dis0,
             const int64_t i = base + lane;
             const bool valid = i < end;
             float v = 0.f;
+            uint32_t my_id = DFX_SEC_NONE;  // loaded with the code: never a dependent load on admission
             if (valid) {
+                my_id = (uint32_t)__ldg(ids + i);
                 // table values of this vector, then the canonical halving tree (oracle pq_sum)
                 constexpr int P = (MT > 0) ? MT : 64;  // MT is a power of two when > 0
                 float val[P];
@@ -331,7 +333,7 @@ scan_pq_kernel(const float* __restrict__ lut, const float* __restrict__ dis0,
                 v = d0 + (__ldg(tvals + i) + val[0]);
             }
             uint32_t sec = 0;
-            const bool want = valid && wt.admits(v, [&] { return (uint32_t)__ldg(ids + i); }, sec);
+            const bool want = valid && wt.admits(v, [&] { return my_id; }, sec);
             wt.push_lanes(want, v, sec);
         }
     }
@@ -381,8 +383,12 @@ scan_rows_kernel(const float* __restrict__ Q, int d, const float* __restrict__ c
         const int64_t beg = list_off[l], end = list_off[l + 1];
         for (int64_t base = beg + warp * U; base < end; base += 4 * U) {
             float acc[U];
+            uint32_t vid[U];
 #pragma unroll
-            for (int u = 0; u < U; u++) acc[u] = 0.f;
+            for (int u = 0; u < U; u++) {
+                acc[u] = 0.f;
+                vid[u] = (base + u < end) ? (uint32_t)__ldg(ids + base + u) : DFX_SEC_NONE;
+            }
             for (int kb = 4 * lane; kb < d; kb += 128) {
                 const float4 qv = *reinterpret_cast<const float4*>(s_q + kb);
                 float4 xv[U];
@@ -427,7 +433,7 @@ scan_rows_kernel(const float* __restrict__ Q, int d, const float* __restrict__ c
                 float v = dfx_warp_butterfly(acc[u]);
                 if (MODE == 0) v = -v;
                 uint32_t sec = 0;
-                if (i < end && wt.admits(v, [&] { return (uint32_t)__ldg(ids + i); }, sec))
+                if (i < end && wt.admits(v, [&] { return vid[u]; }, sec))
                     wt.push_uniform(v, sec);
             }
         }
