@@ -150,7 +150,7 @@ __device__ __forceinline__ uint32_t ld_stream_u(const int32_t* p) {
 
 // lutT: [nq][256][32] (transposed table, written by pq_prep_kernel)
 constexpr int IL_THREADS = 256;  // 8 warps: 4 CTAs/SM = 32 warps/SM (the 64-register limit)
-__global__ void __launch_bounds__(IL_THREADS)
+__global__ void __launch_bounds__(IL_THREADS, 4)
 scan_pq_il_kernel(const float* __restrict__ lutT, const float* __restrict__ dis0, const int32_t* __restrict__ keys,
                   int nprobe, int G, int ngroups, const int64_t* __restrict__ blk_off,
                   const uint4* __restrict__ il_codes, const float* __restrict__ il_tvals,
@@ -177,71 +177,90 @@ scan_pq_il_kernel(const float* __restrict__ lutT, const float* __restrict__ dis0
 #pragma unroll
     for (int t = 0; t < 4; t++) moff[t] = lut_base + (li + 8u * ((t + lu) & 3u)) * 4u;
 
+    // one 32-vector block: 32 conflict-free table lookups, the in-lane part of the tree, the
+    // 8-lane butterfly, then the admission test.  `w` = this lane's 8 code words.
+    auto process = [&](const uint4& ca, const uint4& cb, float tv, uint32_t my_id, float d0) {
+        const uint32_t w[8] = {ca.x, ca.y, ca.z, ca.w, cb.x, cb.y, cb.z, cb.w};
+        float a[8];
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+            float y[4];
+#pragma unroll
+            for (int t = 0; t < 4; t++) {
+                // byte t of the word (one PRMT), times the 128-byte row pitch plus this lane's
+                // column offset (one IMAD)
+                const uint32_t code = __byte_perm(w[r], 0u, 0x4440u + (uint32_t)t);
+                const uint32_t addr = code * 128u + moff[t];
+                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(y[t]) : "r"(addr));
+            }
+            a[r] = (y[0] + y[2]) + (y[1] + y[3]);  // tree levels 16 and 8
+        }
+#pragma unroll
+        for (int off = 4; off >= 1; off >>= 1) {  // tree levels 4, 2, 1 across the 8 lanes
+#pragma unroll
+            for (int r = 0; r < off; r++) a[r] = a[r] + __shfl_xor_sync(0xffffffffu, a[r + off], off);
+        }
+        const float v = d0 + (tv + a[0]);  // vector `lane` of this block; padding has tv = +inf
+        uint32_t sec = 0;
+        const bool want = wt.admits(v, [&] { return my_id; }, sec);
+        wt.push_lanes(want, v, sec);
+    };
+
+    constexpr int S = IL_THREADS / 32;  // block stride of one warp
     const int p_end = min(nprobe, (g + 1) * G);
     for (int p = g * G; p < p_end; p++) {
         const int l = keys[q * nprobe + p];
         if (l < 0) continue;
         const float d0 = dis0[q * nprobe + p];
-        const int64_t bend = blk_off[l + 1];
-        constexpr int S = IL_THREADS / 32;  // block stride of one warp
-        int64_t b = blk_off[l] + warp;
-        // two blocks of look-ahead per warp (codes + t), streaming loads: ~2.3 KB in flight per warp
-        // (the ids ride along: fetching an id only when a candidate is admitted would put a full
-        // DRAM latency on the critical path of every admission)
-        uint4 n0a, n0b, n1a, n1b;
-        float nt0 = 0.f, nt1 = 0.f;
-        uint32_t ni0 = DFX_SEC_NONE, ni1 = DFX_SEC_NONE;
-        if (b < bend) {
-            n0a = ld_stream(il_codes + b * 64 + lane * 2);
-            n0b = ld_stream(il_codes + b * 64 + lane * 2 + 1);
-            nt0 = ld_stream_f(il_tvals + b * 32 + lane);
-            ni0 = ld_stream_u(il_ids + b * 32 + lane);
+        const int64_t b0 = blk_off[l] + warp;
+        const int64_t nb = (blk_off[l + 1] - b0 + S - 1) / S;  // blocks this warp owns in the list
+        if (nb <= 0) continue;
+        // this lane's slice of block i of the warp: codes 2 x 16 B, t 4 B, id 4 B; everything is
+        // streamed two blocks ahead (an id fetched only on admission would put a DRAM latency on
+        // the critical path of every admission)
+        const uint4* pc = il_codes + b0 * 64 + lane * 2;
+        const float* pt = il_tvals + b0 * 32 + lane;
+        const int32_t* pi = il_ids + b0 * 32 + lane;
+        uint4 xa, xb, ya, yb;
+        float xt = 0.f, yt = 0.f;
+        uint32_t xi = DFX_SEC_NONE, yi = DFX_SEC_NONE;
+        xa = ld_stream(pc);
+        xb = ld_stream(pc + 1);
+        xt = ld_stream_f(pt);
+        xi = ld_stream_u(pi);
+        if (nb > 1) {
+            ya = ld_stream(pc + S * 64);
+            yb = ld_stream(pc + S * 64 + 1);
+            yt = ld_stream_f(pt + S * 32);
+            yi = ld_stream_u(pi + S * 32);
         }
-        if (b + S < bend) {
-            n1a = ld_stream(il_codes + (b + S) * 64 + lane * 2);
-            n1b = ld_stream(il_codes + (b + S) * 64 + lane * 2 + 1);
-            nt1 = ld_stream_f(il_tvals + (b + S) * 32 + lane);
-            ni1 = ld_stream_u(il_ids + (b + S) * 32 + lane);
+        int64_t i = 0;
+        for (; i + 2 <= nb; i += 2) {  // two blocks per trip: x then y, each refilled 2 ahead
+            const uint4 ca = xa, cb = xb;
+            const float ct = xt;
+            const uint32_t ci = xi;
+            if (i + 2 < nb) {
+                xa = ld_stream(pc + 2 * S * 64);
+                xb = ld_stream(pc + 2 * S * 64 + 1);
+                xt = ld_stream_f(pt + 2 * S * 32);
+                xi = ld_stream_u(pi + 2 * S * 32);
+            }
+            process(ca, cb, ct, ci, d0);
+            const uint4 da = ya, db = yb;
+            const float dt = yt;
+            const uint32_t di = yi;
+            if (i + 3 < nb) {
+                ya = ld_stream(pc + 3 * S * 64);
+                yb = ld_stream(pc + 3 * S * 64 + 1);
+                yt = ld_stream_f(pt + 3 * S * 32);
+                yi = ld_stream_u(pi + 3 * S * 32);
+            }
+            process(da, db, dt, di, d0);
+            pc += 2 * S * 64;
+            pt += 2 * S * 32;
+            pi += 2 * S * 32;
         }
-        while (b < bend) {
-            const uint32_t w[8] = {n0a.x, n0a.y, n0a.z, n0a.w, n0b.x, n0b.y, n0b.z, n0b.w};
-            const float tv = nt0;
-            const uint32_t my_id = ni0;
-            n0a = n1a;
-            n0b = n1b;
-            nt0 = nt1;
-            ni0 = ni1;
-            const int64_t bn = b + S;
-            if (b + 2 * S < bend) {
-                n1a = ld_stream(il_codes + (b + 2 * S) * 64 + lane * 2);
-                n1b = ld_stream(il_codes + (b + 2 * S) * 64 + lane * 2 + 1);
-                nt1 = ld_stream_f(il_tvals + (b + 2 * S) * 32 + lane);
-                ni1 = ld_stream_u(il_ids + (b + 2 * S) * 32 + lane);
-            }
-            float a[8];
-#pragma unroll
-            for (int r = 0; r < 8; r++) {
-                float y[4];
-#pragma unroll
-                for (int t = 0; t < 4; t++) {
-                    // (code << 7) + per-lane column offset; table rows are 128 bytes
-                    const uint32_t sh = (t == 0) ? (w[r] << 7) : (w[r] >> (8 * t - 7));
-                    const uint32_t addr = (sh & 0x7f80u) + moff[t];
-                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(y[t]) : "r"(addr));
-                }
-                a[r] = (y[0] + y[2]) + (y[1] + y[3]);  // tree levels 16 and 8
-            }
-#pragma unroll
-            for (int off = 4; off >= 1; off >>= 1) {  // tree levels 4, 2, 1 across the 8 lanes
-#pragma unroll
-                for (int r = 0; r < off; r++) a[r] = a[r] + __shfl_xor_sync(0xffffffffu, a[r + off], off);
-            }
-            const float v = d0 + (tv + a[0]);  // vector `lane` of this block; padding has tv = +inf
-            uint32_t sec = 0;
-            const bool want = wt.admits(v, [&] { return my_id; }, sec);
-            wt.push_lanes(want, v, sec);
-            b = bn;
-        }
+        if (i < nb) process(xa, xb, xt, xi, d0);  // odd tail (x holds block i)
     }
     cta_merge_and_write<IL_THREADS>(wt, s_buf, cap, k, part + ((int64_t)q * ngroups + g) * k);
 }
