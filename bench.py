@@ -467,7 +467,8 @@ def main():
         # cross-check on the way: the GPU shard and the oracle agree bit for bit on this sample
         shards[0].nprobe = nprobe
         Dg, Ig = shards[0].search(xq[:args.cpu_queries].cpu().numpy(), K)
-        cb["gpu_equals_oracle"] = bool(np.array_equal(Dg, cb.pop("_D")) and np.array_equal(Ig, cb.pop("_I")))
+        Do_, Io_ = cb.pop("_D"), cb.pop("_I")
+        cb["gpu_equals_oracle"] = bool(np.array_equal(Dg, Do_) and np.array_equal(Ig, Io_))
 
     log("cpu baseline done")
     if rank == 0:

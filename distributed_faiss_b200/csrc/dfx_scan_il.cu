@@ -166,8 +166,10 @@ scan_pq_il_kernel(const float* __restrict__ lutT, const float* __restrict__ dis0
         float4* dst = reinterpret_cast<float4*>(s_lut);
         for (int i = tid; i < 2048; i += IL_THREADS) dst[i] = src[i];
     }
+    __shared__ unsigned int s_cta_key;  // CTA-wide admission bound (see WarpTopK::cta_key)
+    if (tid == 0) s_cta_key = 0xff800000u;  // order-preserving key of +inf: no bound yet
     WarpTopK wt;
-    wt.init(s_buf + (size_t)warp * cap, cap, k);
+    wt.init(s_buf + (size_t)warp * cap, cap, k, &s_cta_key);
     __syncthreads();
     // byte offsets (inside a 128-byte table row) of the 4 subquantizers this lane looks up, in
     // lookup order: m_t = i + 8*((t+u)&3)
@@ -202,7 +204,7 @@ scan_pq_il_kernel(const float* __restrict__ lutT, const float* __restrict__ dis0
         }
         const float v = d0 + (tv + a[0]);  // vector `lane` of this block; padding has tv = +inf
         uint32_t sec = 0;
-        const bool want = wt.admits(v, [&] { return my_id; }, sec);
+        const bool want = (v + 0.0f <= wt.cta_bound()) && wt.admits(v, [&] { return my_id; }, sec);
         wt.push_lanes(want, v, sec);
     };
 
@@ -215,52 +217,30 @@ scan_pq_il_kernel(const float* __restrict__ lutT, const float* __restrict__ dis0
         const int64_t b0 = blk_off[l] + warp;
         const int64_t nb = (blk_off[l + 1] - b0 + S - 1) / S;  // blocks this warp owns in the list
         if (nb <= 0) continue;
-        // this lane's slice of block i of the warp: codes 2 x 16 B, t 4 B, id 4 B; everything is
-        // streamed two blocks ahead (an id fetched only on admission would put a DRAM latency on
-        // the critical path of every admission)
+        // this lane's slice of block i of the warp: codes 2 x 16 B, t 4 B, id 4 B, streamed one
+        // block ahead (an id fetched only on admission would put a DRAM latency on the critical
+        // path of every admission)
         const uint4* pc = il_codes + b0 * 64 + lane * 2;
         const float* pt = il_tvals + b0 * 32 + lane;
         const int32_t* pi = il_ids + b0 * 32 + lane;
-        uint4 xa, xb, ya, yb;
-        float xt = 0.f, yt = 0.f;
-        uint32_t xi = DFX_SEC_NONE, yi = DFX_SEC_NONE;
-        xa = ld_stream(pc);
-        xb = ld_stream(pc + 1);
-        xt = ld_stream_f(pt);
-        xi = ld_stream_u(pi);
-        if (nb > 1) {
-            ya = ld_stream(pc + S * 64);
-            yb = ld_stream(pc + S * 64 + 1);
-            yt = ld_stream_f(pt + S * 32);
-            yi = ld_stream_u(pi + S * 32);
-        }
-        int64_t i = 0;
-        for (; i + 2 <= nb; i += 2) {  // two blocks per trip: x then y, each refilled 2 ahead
+        uint4 xa = ld_stream(pc), xb = ld_stream(pc + 1);
+        float xt = ld_stream_f(pt);
+        uint32_t xi = ld_stream_u(pi);
+        for (int64_t i = 0; i < nb; i++) {
             const uint4 ca = xa, cb = xb;
             const float ct = xt;
             const uint32_t ci = xi;
-            if (i + 2 < nb) {
-                xa = ld_stream(pc + 2 * S * 64);
-                xb = ld_stream(pc + 2 * S * 64 + 1);
-                xt = ld_stream_f(pt + 2 * S * 32);
-                xi = ld_stream_u(pi + 2 * S * 32);
+            if (i + 1 < nb) {  // next block of this warp, in flight while this one is processed
+                pc += S * 64;
+                pt += S * 32;
+                pi += S * 32;
+                xa = ld_stream(pc);
+                xb = ld_stream(pc + 1);
+                xt = ld_stream_f(pt);
+                xi = ld_stream_u(pi);
             }
             process(ca, cb, ct, ci, d0);
-            const uint4 da = ya, db = yb;
-            const float dt = yt;
-            const uint32_t di = yi;
-            if (i + 3 < nb) {
-                ya = ld_stream(pc + 3 * S * 64);
-                yb = ld_stream(pc + 3 * S * 64 + 1);
-                yt = ld_stream_f(pt + 3 * S * 32);
-                yi = ld_stream_u(pi + 3 * S * 32);
-            }
-            process(da, db, dt, di, d0);
-            pc += 2 * S * 64;
-            pt += 2 * S * 32;
-            pi += 2 * S * 32;
         }
-        if (i < nb) process(xa, xb, xt, xi, d0);  // odd tail (x holds block i)
     }
     cta_merge_and_write<IL_THREADS>(wt, s_buf, cap, k, part + ((int64_t)q * ngroups + g) * k);
 }

@@ -13,13 +13,23 @@ struct WarpTopK {
     int cap, k, cnt;
     float thr;         // value of the current k-th best (+inf until k candidates are held)
     uint32_t thr_sec;  // its secondary key: an equal value is only admitted with a smaller one
-    __device__ __forceinline__ void init(uint64_t* b, int cap_, int k_) {
+    // optional CTA-wide bound: the smallest k-th-best value any warp of the CTA has reached so
+    // far (monotone uint key in shared memory).  Every warp's k-th best is an upper bound of the
+    // CTA's k-th best, so a candidate above it can never be in the CTA's result; candidates equal
+    // to it are still admitted (their rank is decided by the id at merge time).
+    unsigned int* cta_key = nullptr;
+    __device__ __forceinline__ void init(uint64_t* b, int cap_, int k_, unsigned int* cta_key_ = nullptr) {
         buf = b;
         cap = cap_;
         k = k_;
         cnt = 0;
         thr = __int_as_float(0x7f800000);  // +inf
         thr_sec = DFX_SEC_NONE;
+        cta_key = cta_key_;
+    }
+    // current CTA-wide bound as a float (call once per block of work, it is one broadcast LDS)
+    __device__ __forceinline__ float cta_bound() const {
+        return cta_key ? dfx_key2f(*reinterpret_cast<volatile unsigned int*>(cta_key)) : __int_as_float(0x7f800000);
     }
     // does (v, sec) beat the current k-th best?  `sec` is fetched lazily: only on a value tie
     template <class SecFn>
@@ -59,6 +69,7 @@ struct WarpTopK {
             const uint64_t kth = buf[k - 1];
             thr = dfx_key2f((uint32_t)(kth >> 32));
             thr_sec = (uint32_t)kth;
+            if (cta_key && (threadIdx.x & 31) == 0) atomicMin(cta_key, (unsigned int)(kth >> 32));
         }
         __syncwarp();
     }
