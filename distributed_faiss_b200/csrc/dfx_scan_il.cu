@@ -161,16 +161,40 @@ scan_pq_il_kernel(const float* __restrict__ lutT, const float* __restrict__ dis0
     const int64_t q = blockIdx.x / ngroups;
     const int g = blockIdx.x % ngroups;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    {
-        const float4* src = reinterpret_cast<const float4*>(lutT + q * 8192);
-        float4* dst = reinterpret_cast<float4*>(s_lut);
-        for (int i = tid; i < 2048; i += IL_THREADS) dst[i] = src[i];
-    }
+    // the 32 KB table of this query arrives by ONE bulk async copy (TMA engine, mbarrier
+    // completion): no LDG/STS traffic on the LSU pipe that the lookups need
+    __shared__ __align__(8) uint64_t s_lut_bar;
     __shared__ unsigned int s_cta_key;  // CTA-wide admission bound (see WarpTopK::cta_key)
-    if (tid == 0) s_cta_key = 0xff800000u;  // order-preserving key of +inf: no bound yet
+    const uint32_t bar_addr = (uint32_t)__cvta_generic_to_shared(&s_lut_bar);
+    if (tid == 0) {
+        s_cta_key = 0xff800000u;  // order-preserving key of +inf: no bound yet
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_addr) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_addr), "r"(32768u)
+                     : "memory");
+        asm volatile(
+            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+            ::"r"((uint32_t)__cvta_generic_to_shared(s_lut)), "l"(lutT + q * 8192), "r"(32768u), "r"(bar_addr)
+            : "memory");
+    }
     WarpTopK wt;
     wt.init(s_buf + (size_t)warp * cap, cap, k, &s_cta_key);
-    __syncthreads();
+    {
+        uint32_t done;
+        do {
+            asm volatile(
+                "{\n\t.reg .pred p;\n\t"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                "selp.u32 %0, 1, 0, p;\n\t}"
+                : "=r"(done)
+                : "r"(bar_addr), "r"(0u)
+                : "memory");
+        } while (!done);
+    }
     // byte offsets (inside a 128-byte table row) of the 4 subquantizers this lane looks up, in
     // lookup order: m_t = i + 8*((t+u)&3)
     const uint32_t li = lane & 7, lu = lane >> 3;

@@ -361,51 +361,101 @@ __device__ __forceinline__ float screen_tol(float qn2, float cmax2) {
     return 1e-4f * (sqrtf(qn2 * cmax2) + cmax2) + 1e-30f;
 }
 
-// The G smallest group minima of a row, ascending by (value, group), for any G <= ng: one warp
-// per row keeps its NPL = ng/32 values in registers and extracts the minimum G times (each round
-// takes the smallest (value, index) pair above the previous one).  Same result as the generic
-// selection kernel at a fraction of the cost when G << ng.
-template <int NPL>
+// The G (<= 32) smallest group minima of a row, ascending by (value, group): one warp per row.
+//   1. every lane takes the minimum of its ng/32 values; the G-th smallest of those 32 lane
+//      minima, B, bounds the answer from above (G different lanes hold a value <= B);
+//   2. the values <= B are collected (a few dozen at most in practice) into a per-warp buffer;
+//   3. the buffer is bitonic-sorted by the warp and the first G entries are written.
+// Exact for any input; if more than CAP values are <= B (massive ties) the row falls back to
+// G rounds of warp arg-min.  ~10x fewer instructions than G x ng compare rounds.
+template <int CAP>
 __global__ void __launch_bounds__(256)
-topg_warp_kernel(const float* __restrict__ gmin, int64_t nq, int ng, int G, int32_t* __restrict__ groups) {
-    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
+topg_collect_kernel(const float* __restrict__ gmin, int64_t nq, int ng, int G, int32_t* __restrict__ groups) {
+    __shared__ uint64_t s_buf[8][CAP];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * 8 + warp;
     if (row >= nq) return;
     const float* g = gmin + row * ng;
-    const float inf = __int_as_float(0x7f800000);
-    float v[NPL];
-#pragma unroll
-    for (int i = 0; i < NPL; i++) {
-        const int j = lane + 32 * i;
-        v[i] = (j < ng) ? (g[j] + 0.0f) : inf;
+    uint64_t* buf = s_buf[warp];
+    // 1. lane minima -> bound
+    uint64_t lmin = DFX_COMP_NONE;
+    for (int j = lane; j < ng; j += 32) {
+        const uint64_t c = dfx_comp(g[j], (uint32_t)j);
+        lmin = c < lmin ? c : lmin;
     }
-    float pv = -inf;
-    int pj = -1;
-    for (int r = 0; r < G; r++) {
-        float bv = inf;
-        int bj = 0x7fffffff;
+    // bitonic sort of the 32 lane minima across the warp (ascending by lane)
+    uint64_t x = lmin;
 #pragma unroll
-        for (int i = 0; i < NPL; i++) {
-            const int j = lane + 32 * i;
-            const bool after = (v[i] > pv) || (v[i] == pv && j > pj);  // strictly after the previous pick
-            if (after && v[i] < bv && j < ng) {                          // ascending i: smallest j wins ties
-                bv = v[i];
-                bj = j;
+    for (int size = 2; size <= 32; size <<= 1) {
+#pragma unroll
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            const uint64_t y = __shfl_xor_sync(0xffffffffu, x, stride);
+            const bool up = ((lane & size) == 0);
+            const bool lower = ((lane & stride) == 0);
+            const bool take_min = (lower == up);
+            x = take_min ? (x < y ? x : y) : (x < y ? y : x);
+        }
+    }
+    const int gth = min(G, 32) - 1;
+    const uint64_t bound = __shfl_sync(0xffffffffu, x, gth);  // G-th smallest lane minimum
+    // 2. collect everything <= bound
+    int cnt = 0;
+    bool overflow = false;
+    for (int j0 = 0; j0 < ng; j0 += 32) {
+        const int j = j0 + lane;
+        const uint64_t c = (j < ng) ? dfx_comp(g[j], (uint32_t)j) : DFX_COMP_NONE;
+        const bool want = c <= bound && c != DFX_COMP_NONE;
+        const unsigned mask = __ballot_sync(0xffffffffu, want);
+        if (mask) {
+            const int pos = cnt + __popc(mask & ((1u << lane) - 1u));
+            if (want && pos < CAP) buf[pos] = c;
+            cnt += __popc(mask);
+            if (cnt > CAP) overflow = true;
+        }
+    }
+    if (!overflow) {
+        // 3. sort the candidates
+        int P = 32;
+        while (P < cnt) P <<= 1;
+        for (int e = cnt + lane; e < P; e += 32) buf[e] = DFX_COMP_NONE;
+        __syncwarp();
+        for (int size = 2; size <= P; size <<= 1) {
+            for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                for (int i = lane; i < (P >> 1); i += 32) {
+                    const int pos = 2 * i - (i & (stride - 1));
+                    const int partner = pos + stride;
+                    const bool up = ((pos & size) == 0);
+                    const uint64_t a = buf[pos], bb = buf[partner];
+                    if ((a > bb) == up) {
+                        buf[pos] = bb;
+                        buf[partner] = a;
+                    }
+                }
+                __syncwarp();
             }
+        }
+        for (int r = lane; r < G; r += 32) {
+            const uint64_t c = (r < P) ? buf[r] : DFX_COMP_NONE;
+            groups[row * G + r] = (c == DFX_COMP_NONE) ? -1 : (int32_t)(uint32_t)c;
+        }
+        return;
+    }
+    // fallback: G rounds of "smallest composite above the previous pick"
+    uint64_t prev = 0;
+    for (int r = 0; r < G; r++) {
+        uint64_t best = DFX_COMP_NONE;
+        for (int j = lane; j < ng; j += 32) {
+            const uint64_t c = dfx_comp(g[j], (uint32_t)j);
+            if ((r == 0 || c > prev) && c < best) best = c;
         }
 #pragma unroll
         for (int off = 16; off >= 1; off >>= 1) {
-            const float ov = __shfl_xor_sync(0xffffffffu, bv, off);
-            const int oj = __shfl_xor_sync(0xffffffffu, bj, off);
-            if (ov < bv || (ov == bv && oj < bj)) {
-                bv = ov;
-                bj = oj;
-            }
+            const uint64_t o = __shfl_xor_sync(0xffffffffu, best, off);
+            best = o < best ? o : best;
         }
-        if (lane == 0) groups[row * G + r] = (bj == 0x7fffffff) ? -1 : bj;
-        pv = bv;
-        pj = bj;
-        if (bj == 0x7fffffff) pv = inf;  // exhausted: every later round yields -1 as well
+        if (lane == 0) groups[row * G + r] = (best == DFX_COMP_NONE) ? -1 : (int32_t)(uint32_t)best;
+        prev = best;
+        if (best == DFX_COMP_NONE) prev = DFX_COMP_NONE - 1;
     }
 }
 
@@ -602,11 +652,26 @@ static void tc_screen(dfx_index* idx, int d, const float* d_x, int64_t nq, const
     const int qtiles = (int)(nq_pad / TILE), ctiles = (int)(nl_pad / TILE);
     // enough CTAs to fill the machine a few times over, each walking a contiguous range of
     // centroid tiles with its query tile resident
-    int csplit = (int)dfx_ceil_div(4 * 148, qtiles);
-    if (csplit > ctiles) csplit = ctiles;
-    if (csplit < 1) csplit = 1;
-    const int per = (int)dfx_ceil_div(ctiles, csplit);
-    csplit = (int)dfx_ceil_div(ctiles, per);
+    // split the centroid tiles so that the grid is close to a whole number of 148-CTA waves
+    // (one CTA per SM) while every CTA keeps enough tiles to amortise loading its query tile:
+    // cost model = waves x (tiles per CTA + ~3 tiles of fixed overhead)
+    int csplit = 1, per = ctiles;
+    {
+        double best_cost = 1e30;
+        for (int cs = 1; cs <= ctiles && cs <= 4096; cs++) {
+            const int pr = (int)dfx_ceil_div(ctiles, cs);
+            const int cs_eff = (int)dfx_ceil_div(ctiles, pr);
+            if (cs_eff != cs) continue;
+            const int64_t ctas = (int64_t)qtiles * cs;
+            const double waves = (double)dfx_ceil_div(ctas, 148);
+            const double cost = waves * (pr + 3.0);
+            if (cost < best_cost - 1e-9) {
+                best_cost = cost;
+                csplit = cs;
+                per = pr;
+            }
+        }
+    }
     const int katoms = d / KATOM;
     const size_t smem = (size_t)Smem::total(katoms) + 1024;
     dim3 grid((unsigned)csplit, (unsigned)qtiles);
@@ -643,12 +708,8 @@ void dfx_tc_coarse_search(dfx_index* idx, const float* d_x, int64_t nq, int npro
         const int64_t qc = std::min(QC, nq - q0);
         tc_screen(idx, d, d_x + q0 * d, qc, idx->tc_cent.p, idx->cnorm.as<float>(), nlist, idx->cfg.metric,
                   idx->tc_gmin.as<float>(), idx->tc_gmin2.as<float>(), idx->tc_gargc.as<uint8_t>(), st);
-        if (ng <= 512 && G <= 64) {
-            auto tk = topg_warp_kernel<16>;
-            DFX_LAUNCH(tk, (unsigned)dfx_ceil_div(qc, 8), 256, 0, st, idx->tc_gmin.as<float>(), qc, ng, G,
-                       idx->tc_groups.as<int32_t>());
-        } else if (ng <= 2048 && G <= 64) {
-            auto tk = topg_warp_kernel<64>;
+        if (G <= 32 && ng >= 32) {
+            auto tk = topg_collect_kernel<256>;
             DFX_LAUNCH(tk, (unsigned)dfx_ceil_div(qc, 8), 256, 0, st, idx->tc_gmin.as<float>(), qc, ng, G,
                        idx->tc_groups.as<int32_t>());
         } else {
