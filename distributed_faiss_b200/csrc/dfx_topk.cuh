@@ -92,14 +92,35 @@ struct WarpTopK {
     }
 };
 
-// merges the per-warp sets of a CTA and writes k composites (NONE padded) to out
+// merges the per-warp sets of a CTA and writes k composites (NONE padded) to out.
+// Each warp first sorts and cuts its own set to <= k entries; only those live entries
+// (NW*k of the NW*cap slots) are then packed densely and sorted by the CTA.
 template <int THREADS>
 __device__ __forceinline__ void cta_merge_and_write(WarpTopK& wt, uint64_t* s_buf, int cap, int k,
                                                     uint64_t* out) {
-    wt.sort_and_cut();  // leaves [cnt, cap) == NONE
-    __syncthreads();
+    wt.sort_and_cut();
     constexpr int NW = THREADS / 32;
-    dfx_block_bitonic_sort<THREADS>(s_buf, NW * cap);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (k <= 128) {
+        uint64_t mine[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int j = lane + 32 * i;
+            mine[i] = (j < wt.cnt) ? wt.buf[j] : DFX_COMP_NONE;
+        }
+        __syncthreads();  // every warp has its live entries in registers: s_buf can be reused
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int j = lane + 32 * i;
+            if (j < k) s_buf[warp * k + j] = mine[i];
+        }
+        int P = 32;
+        while (P < NW * k) P <<= 1;
+        for (int e = NW * k + threadIdx.x; e < P; e += THREADS) s_buf[e] = DFX_COMP_NONE;
+        dfx_block_bitonic_sort<THREADS>(s_buf, P);
+    } else {
+        __syncthreads();
+        dfx_block_bitonic_sort<THREADS>(s_buf, NW * cap);
+    }
     for (int j = threadIdx.x; j < k; j += THREADS) out[j] = s_buf[j];
 }
-
