@@ -78,6 +78,13 @@ class ShardGroup:
         self._pin_q = None
         self._pin_D = None
         self._pin_I = None
+        # side streams for intra-rank shard overlap (CUDA backend only)
+        self._streams = []
+        if self.device.type == "cuda" and isinstance(self.backend, CudaBackend) and len(self.shards) > 1:
+            import os
+
+            n_side = int(os.environ.get("DFX_SHARD_STREAMS", "2"))
+            self._streams = [torch.cuda.Stream(device=self.device) for _ in range(max(0, n_side))]
 
     @property
     def num_shards(self) -> int:
@@ -106,8 +113,27 @@ class ShardGroup:
         S_loc = len(self.shards)
         D_loc = torch.empty((S_loc, nq, k), dtype=torch.float32, device=x_t.device)
         I_loc = torch.empty((S_loc, nq, k), dtype=torch.int64, device=x_t.device)
-        for j, shard in enumerate(self.shards):
-            self.backend.search_into(shard, x_t, k, D_loc[j], I_loc[j], self.id_tables[j])
+        if self._streams and S_loc > 1:
+            # shards of one rank are independent: alternate them over a few side streams so the
+            # short kernels of one shard (table build, re-rank, selection) fill the tail of
+            # another shard's list scan
+            main = torch.cuda.current_stream(x_t.device)
+            ready = torch.cuda.Event()
+            ready.record(main)
+            for j, shard in enumerate(self.shards):
+                st = self._streams[j % len(self._streams)]
+                if j < len(self._streams):
+                    st.wait_event(ready)
+                with torch.cuda.stream(st):
+                    self.backend.search_into(shard, x_t, k, D_loc[j], I_loc[j], self.id_tables[j])
+            for st in self._streams[:min(len(self._streams), S_loc)]:
+                done = torch.cuda.Event()
+                done.record(st)
+                main.wait_event(done)
+            D_loc.record_stream(main)
+        else:
+            for j, shard in enumerate(self.shards):
+                self.backend.search_into(shard, x_t, k, D_loc[j], I_loc[j], self.id_tables[j])
         if self.world > 1:
             D_all = torch.empty((self.world * S_loc, nq, k), dtype=torch.float32, device=x_t.device)
             I_all = torch.empty((self.world * S_loc, nq, k), dtype=torch.int64, device=x_t.device)
