@@ -80,10 +80,14 @@ class ShardGroup:
         self._pin_I = None
         # side streams for intra-rank shard overlap (CUDA backend only)
         self._streams = []
+        self._stream_max_nq = 0
         if self.device.type == "cuda" and isinstance(self.backend, CudaBackend) and len(self.shards) > 1:
             import os
 
-            n_side = int(os.environ.get("DFX_SHARD_STREAMS", "2"))
+            # latency-bound batches gain ~1.8x from overlapping the shards; large batches already
+            # fill the machine and are run back to back (also keeps per-kernel timing clean)
+            self._stream_max_nq = int(os.environ.get("DFX_SHARD_STREAMS_MAX_NQ", "1024"))
+            n_side = int(os.environ.get("DFX_SHARD_STREAMS", "4"))
             self._streams = [torch.cuda.Stream(device=self.device) for _ in range(max(0, n_side))]
 
     @property
@@ -113,7 +117,7 @@ class ShardGroup:
         S_loc = len(self.shards)
         D_loc = torch.empty((S_loc, nq, k), dtype=torch.float32, device=x_t.device)
         I_loc = torch.empty((S_loc, nq, k), dtype=torch.int64, device=x_t.device)
-        if self._streams and S_loc > 1:
+        if self._streams and S_loc > 1 and nq <= self._stream_max_nq:
             # shards of one rank are independent: alternate them over a few side streams so the
             # short kernels of one shard (table build, re-rank, selection) fill the tail of
             # another shard's list scan
