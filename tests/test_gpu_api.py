@@ -18,6 +18,19 @@ def free_port():
         return s.getsockname()[1]
 
 
+def wait_listening(ports, timeout=30.0):
+    """block until every server thread accepts connections (start_blocking runs in a thread)"""
+    t0 = time.time()
+    for p in ports:
+        while True:
+            try:
+                socket.create_connection(("localhost", p), timeout=1.0).close()
+                break
+            except OSError:
+                assert time.time() - t0 < timeout, f"server on port {p} never came up"
+                time.sleep(0.05)
+
+
 def make_client(ports):
     from distributed_faiss_b200.client import IndexClient
 
@@ -54,7 +67,7 @@ def cluster():
     sp = free_port()
     single = IndexServer(0, dirs[1].name)
     threading.Thread(target=single.start_blocking, args=(sp,), daemon=True).start()
-    time.sleep(0.3)
+    wait_listening(ports + [sp])
     yield {"ports": ports, "single": sp, "dirs": dirs}
     for s in servers + [single]:
         s.stop()

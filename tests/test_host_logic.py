@@ -49,11 +49,24 @@ def cluster():
     single_port = free_port()
     single = IndexServer(0, dirs[1].name, engine_factory=oracle_engine_factory)
     threading.Thread(target=single.start_blocking, args=(single_port,), daemon=True).start()
-    time.sleep(0.3)
+    wait_listening(multi_ports + [single_port])
     yield {"multi_ports": multi_ports, "single_port": single_port, "servers": servers, "single": single,
            "dirs": dirs}
     for s in servers + [single]:
         s.stop()
+
+
+def wait_listening(ports, timeout=30.0):
+    """block until every server thread accepts connections (start_blocking runs in a thread)"""
+    t0 = time.time()
+    for p in ports:
+        while True:
+            try:
+                socket.create_connection(("localhost", p), timeout=1.0).close()
+                break
+            except OSError:
+                assert time.time() - t0 < timeout, f"server on port {p} never came up"
+                time.sleep(0.05)
 
 
 def make_client(ports):
