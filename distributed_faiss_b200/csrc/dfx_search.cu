@@ -203,6 +203,7 @@ pq_prep_kernel(const float* __restrict__ Q, int d, int M, int ksub, int dsub,
     __syncthreads();
     if (lut) {
         const int tot = M * ksub;
+#pragma unroll 4
         for (int idx = threadIdx.x; idx < tot; idx += blockDim.x) {
             const int m = (ksub == 256) ? (idx >> 8) : (idx / ksub);
             const float* p = codebooks + (size_t)idx * dsub;

@@ -47,11 +47,15 @@ struct WarpTopK {
     }
     __device__ __forceinline__ void sort_and_cut() {
         const int lane = threadIdx.x & 31;
-        for (int e = cnt + lane; e < cap; e += 32) buf[e] = DFX_COMP_NONE;
+        // sort only as many slots as are live (rounded up to a power of two, >= 32); slots
+        // beyond P are never read before they are overwritten by later pushes
+        int P = 32;
+        while (P < cnt) P <<= 1;
+        for (int e = cnt + lane; e < P; e += 32) buf[e] = DFX_COMP_NONE;
         __syncwarp();
-        for (int size = 2; size <= cap; size <<= 1) {
+        for (int size = 2; size <= P; size <<= 1) {
             for (int stride = size >> 1; stride > 0; stride >>= 1) {
-                for (int i = lane; i < (cap >> 1); i += 32) {
+                for (int i = lane; i < (P >> 1); i += 32) {
                     int pos = 2 * i - (i & (stride - 1));
                     int partner = pos + stride;
                     bool up = ((pos & size) == 0);
@@ -119,6 +123,8 @@ __device__ __forceinline__ void cta_merge_and_write(WarpTopK& wt, uint64_t* s_bu
         for (int e = NW * k + threadIdx.x; e < P; e += THREADS) s_buf[e] = DFX_COMP_NONE;
         dfx_block_bitonic_sort<THREADS>(s_buf, P);
     } else {
+        // full-width path: everything beyond each warp's live entries must read as "none"
+        for (int e = wt.cnt + lane; e < cap; e += 32) wt.buf[e] = DFX_COMP_NONE;
         __syncthreads();
         dfx_block_bitonic_sort<THREADS>(s_buf, NW * cap);
     }

@@ -131,7 +131,7 @@ def test_ivf_matches_oracle(kind, metric, d, nlist, M, via):
     xq = np.concatenate([clustered(rs, 20, d, ncl=8), xb[:5] + 0.01 * rs.randn(5, d).astype(np.float32)])
     for nprobe in (nlist, 1, 5):  # full nprobe first: the north-star parity condition
         g.nprobe = nprobe; o.nprobe = nprobe
-        for k in (10, 1, 100):
+        for k in (10, 1, 100, 300):  # 300 > 128: the full-width CTA merge path
             Dg, Ig = g.search(xq, k)
             Do, Io = o.search(xq, k)
             _assert_same(Dg, Ig, Do, Io, f"{kind} metric={metric} d={d} via={via} nprobe={nprobe} k={k}")
