@@ -458,8 +458,16 @@ def main():
     bytes_per_launch /= launches_per_search
     achieved = bytes_per_launch / (per_launch_ms * 1e-3) / 1e9 if per_launch_ms > 0 else 0.0
     scan_ms_per_step = scan_ms / (args.steps + args.warmup)
+    # DRAM traffic of the same kernel from the committed ncu --set full capture (same command)
+    traffic = None
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_scan_traffic.json")))
+        if tr["when"] == {"nvec": nvec, "batch": B, "nprobe": nprobe} and world == 1:
+            traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
+    except Exception:
+        pass
     roofline = {"kernel": "scan_pq_il_kernel (IVF-PQ list scan, interleaved M=32)", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "bytes_per_launch": bytes_per_launch, "ms_per_launch": per_launch_ms,
                 "launches_per_step": scan_launches / (args.steps + args.warmup),
                 "scan_share_of_step": scan_ms_per_step / (ms / args.steps) if ms else None}
