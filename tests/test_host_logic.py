@@ -316,3 +316,61 @@ def test_many_clients_one_server(cluster):
     [t.start() for t in threads]
     [t.join(60) for t in threads]
     assert not errors, errors
+
+
+def test_config_to_file_and_nprobe_override(cluster):
+    """reference tests/test_integration.py:332-385: cfg.json is written next to the shard, a load
+    without cfg reads it back, a cfg given at load time overrides nprobe on the live index."""
+    index_id = "t_cfgfile"
+    rs = np.random.RandomState(5)
+    d = 16
+    cfg = IndexCfg(index_builder_type="ivf_simple", dim=d, centroids=4, metric="l2", nprobe=2, train_num=200)
+    client = make_client([cluster["single_port"]])
+    client.create_index(index_id, cfg)
+    x = rs.rand(300, d).astype(np.float32)
+    client.add_index_data(index_id, x, list(range(300)), False)
+    wait_trained(client, index_id)
+    client.save_index(index_id)
+    cfg_path = os.path.join(cluster["dirs"][1].name, index_id, "0", "cfg.json")
+    on_disk = IndexCfg.from_json(cfg_path)
+    assert on_disk.nprobe == 2 and on_disk.centroids == 4 and on_disk.index_builder_type == "ivf_simple"
+    D_before, m_before = client.search(x[:5], 3, index_id)
+    client.close()
+    c2 = make_client([cluster["single_port"]])
+    assert c2.load_index(index_id)                                   # cfg comes from the file
+    assert c2.cfg.nprobe == 2 and c2.cfg.metric == "l2"
+    D_after, m_after = c2.search(x[:5], 3, index_id)
+    assert np.array_equal(D_before, D_after) and m_before == m_after  # reloaded shard answers identically
+    cfg2 = IndexCfg(index_builder_type="ivf_simple", dim=d, centroids=4, metric="l2", nprobe=3)
+    assert c2.load_index(index_id, cfg2, force_reload=False)          # already loaded: cfg is applied
+    assert cluster["single"].indexes[index_id].faiss_index.nprobe == 3
+    c2.close()
+
+
+def test_flat_builder_ignores_l2_metric(cluster):
+    """SURVEY quirk B1 (reference index.py:94 + client.py:206): the "flat" builder is always an
+    inner-product index; with metric="l2" each shard still returns its LARGEST inner products and
+    the client merges them keeping the SMALLEST, un-negated.  Reproduced, not fixed."""
+    from oracle import oracle as O
+
+    index_id = "t_l2_flat"
+    rs = np.random.RandomState(6)
+    d = 16
+    cfg = IndexCfg(index_builder_type="flat", dim=d, metric="l2")
+    client = make_client(cluster["multi_ports"])
+    client.create_index(index_id, cfg)
+    shards = []
+    for s in range(4):
+        x = rs.rand(50, d).astype(np.float32)
+        shards.append(x)
+        client.add_index_data(index_id, x, [f"s{s}_{i}" for i in range(50)], False)
+    client.sync_train(index_id)
+    wait_trained(client, index_id)
+    q = rs.rand(3, d).astype(np.float32)
+    D, meta = client.search(q, 2, index_id)
+    # expected by hand from the rule above
+    per_shard = [O.flat_search(O.METRIC_IP, x, q, 2)[0] for x in shards]  # top-2 largest IP per shard
+    pool = np.concatenate(per_shard, axis=1)                               # [3, 8]
+    expect = np.sort(pool, axis=1)[:, :2]
+    assert np.array_equal(D, expect) and (D > 0).all()
+    client.close()
