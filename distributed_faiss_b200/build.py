@@ -17,7 +17,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libdfx.so")
-SOURCES = ["dfx_api.cu", "dfx_search.cu", "dfx_build.cu", "dfx_tc.cu", "dfx_scan_il.cu"]
+SOURCES = ["dfx_api.cu", "dfx_search.cu", "dfx_build.cu", "dfx_tc.cu", "dfx_scan_il.cu", "dfx_scan_il2.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

@@ -1,5 +1,6 @@
 // dfx_api.cu -- extern "C" surface of libdfx.so (include/dfx.h) + synthetic data generator.
 #include "dfx_internal.h"
+#include <cstdlib>
 #include <cstring>
 #include <cmath>
 #include <vector>
@@ -52,6 +53,7 @@ extern "C" {
 const char* dfx_last_error(void) { return g_last_error.c_str(); }
 const char* dfx_version(void) { return "dfx 0.1 (sm_100a)"; }
 int64_t dfx_launch_count(void) { return (int64_t)g_dfx_launches.load(); }
+int dfx_debug_il_byte(int layout, int v, int m) { return dfx_il_byte_of(layout, v & 31, m & 31); }
 
 int dfx_create(const dfx_cfg* cfg, dfx_index** out) {
     DFX_API_BEGIN
@@ -75,6 +77,9 @@ int dfx_create(const dfx_cfg* cfg, dfx_index** out) {
         idx->M = cfg->pq_m;
         idx->ksub = 256;
         idx->dsub = cfg->d / cfg->pq_m;
+        // experiments: DFX_SCAN_VARIANT=2 makes new indexes start on the lane-per-vector scan
+        if (const char* e = getenv("DFX_SCAN_VARIANT"))
+            if (atoi(e) == 2) idx->il_variant = 2;
     }
     DeviceGuard g(cfg->device);
     DFX_CUDA(cudaStreamCreateWithFlags(&idx->stream, cudaStreamNonBlocking));
@@ -112,6 +117,16 @@ int dfx_set_param(dfx_index* idx, const char* name, double value) {
         idx->il_enabled = value != 0;
         if (!idx->il_enabled) dfx_pq_il_to_rm(idx, idx->stream);
         else if (idx->trained && idx->n_pending == 0 && idx->n_sorted > 0) dfx_pq_rm_to_il(idx, idx->stream);
+    }
+    else if (n == "scan_variant") {
+        // 1 = scan_pq_il_kernel (8 lanes per vector), 2 = scan_pq_il2_kernel (lane per vector,
+        // wide table); changes the block layout, so resident blocks are converted
+        DFX_REQUIRE(value == 1 || value == 2, "scan_variant must be 1 or 2");
+        std::lock_guard<std::mutex> lk(idx->mu);
+        DeviceGuard g(idx->cfg.device);
+        idx->join_dev();
+        idx->il_variant = (int)value;
+        if (idx->il && idx->il_layout != idx->il_variant) dfx_pq_rm_to_il(idx, idx->stream);
     }
     else throw DfxError{"unknown parameter " + n};
     DFX_API_END

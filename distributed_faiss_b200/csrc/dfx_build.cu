@@ -526,8 +526,8 @@ __global__ void invert_ids_kernel(const int32_t* __restrict__ ids, int64_t n, in
     if (i < n && ids[i] >= 0) inv[ids[i]] = (int32_t)i;
 }
 
-// il != 0 (IVF-PQ interleaved): `inv` holds padded block positions and codes are read from
-// the interleaved blocks (dfx_il_byte(pos%32, m) of block pos/32)
+// il != 0 (IVF-PQ interleaved, il = block layout 1 or 2): `inv` holds padded block positions and
+// codes are read from the interleaved blocks (dfx_il_byte_of(il, pos%32, m) of block pos/32)
 __global__ void reconstruct_kernel(int kind, int d, int M, int ksub, int dsub, int64_t ntotal,
                                    int64_t nlist, const int64_t* __restrict__ want,
                                    const int32_t* __restrict__ inv, const void* __restrict__ rows,
@@ -561,7 +561,7 @@ __global__ void reconstruct_kernel(int kind, int d, int M, int ksub, int dsub, i
         } else {
             int m = k / dsub;
             int code;
-            if (il) code = reinterpret_cast<const uint8_t*>(rows)[(pos >> 5) * 1024 + dfx_il_byte((int)(pos & 31), m)];
+            if (il) code = reinterpret_cast<const uint8_t*>(rows)[(pos >> 5) * 1024 + dfx_il_byte_of(il, (int)(pos & 31), m)];
             else code = reinterpret_cast<const uint8_t*>(rows)[pos * M + m];
             v = cent[(size_t)l * d + k] + codebooks[((size_t)m * ksub + code) * dsub + (k - m * dsub)];
         }
@@ -574,7 +574,7 @@ void dfx_reconstruct_impl(dfx_index* idx, int64_t n, const int64_t* d_ids, float
     if (n <= 0) return;
     if (idx->n_pending > 0) dfx_finalize_impl(idx, st);
     const int64_t nt = idx->n_sorted;
-    const int il = idx->il ? 1 : 0;
+    const int il = idx->il ? idx->il_layout : 0;  // 0 = row-major, else the block layout
     if (idx->is_ivf() && !idx->inv_valid) {
         idx->inv.reserve((size_t)std::max<int64_t>(nt, 1) * 4);
         const int64_t npos = il ? idx->nblk * 32 : nt;

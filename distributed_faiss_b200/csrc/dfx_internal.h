@@ -40,6 +40,10 @@ struct dfx_index {
     bool il = false, il_enabled = true;
     DevBuf il_codes, il_tvals, il_ids, blk_off;
     int64_t nblk = 0;
+    // which block layout / scan kernel: 1 = dfx_il_byte + scan_pq_il_kernel (default),
+    // 2 = dfx_il2_byte + scan_pq_il2_kernel (dfx_scan_il2.cu; dfx_set_param "scan_variant")
+    int il_variant = 1;  // requested
+    int il_layout = 0;   // layout the il_* arrays currently hold (valid while `il`)
 
     // tensor-core coarse quantizer (dfx_tc.cu): bf16 hi/lo planes and screening workspace
     DevBuf tc_cent, tc_cent_tmp, tc_q, tc_gmin, tc_gmin2, tc_gargc, tc_groups, tc_cand, tc_qn, tc_amb;
@@ -122,12 +126,29 @@ __host__ __device__ __forceinline__ int dfx_il_byte(int v, int m) {
     return (8 * u + i) * 32 + (w ^ i) * 4 + ((j - u) & 3);
 }
 
+// Layout 2 (dfx_scan_il2.cu): one lane per vector.  Lane v of the scanning warp owns vector v of
+// the block and walks its 32 subquantizers in the rotated order m = (t + v) & 31, t = 0..31, so
+// that at every step the 32 lanes read 32 different table columns (bank == column).  Byte t of
+// the lane's 32 code bytes therefore holds the code of subquantizer (t + v) & 31; the two 16-byte
+// halves of all lanes are stored contiguously (bytes 0..511: t = 0..15 of lanes 0..31, bytes
+// 512..1023: t = 16..31) so that each of the two 128-bit loads of a warp is one 512-byte run.
+__host__ __device__ __forceinline__ int dfx_il2_byte(int v, int m) {
+    const int t = (m - v) & 31;
+    return (t >> 4) * 512 + v * 16 + (t & 15);
+}
+__host__ __device__ __forceinline__ int dfx_il_byte_of(int layout, int v, int m) {
+    return layout == 2 ? dfx_il2_byte(v, m) : dfx_il_byte(v, m);
+}
+
 // ---- dfx_scan_il.cu
 bool dfx_il_wanted(const dfx_index* idx);
 void dfx_pq_rm_to_il(dfx_index* idx, cudaStream_t st);
 void dfx_pq_il_to_rm(dfx_index* idx, cudaStream_t st);
 void dfx_launch_scan_pq_il(dfx_index* idx, int64_t qc, const int32_t* keys, int nprobe, int G, int ngroups,
                            int k, int cap, uint64_t* part, cudaStream_t st);
+// ---- dfx_scan_il2.cu  (lutW: [nq][256][64] wide table, see pq_prep_kernel mode 2)
+void dfx_launch_scan_pq_il2(dfx_index* idx, int64_t qc, const int32_t* keys, int nprobe, int G, int ngroups,
+                            int k, int cap, uint64_t* part, cudaStream_t st);
 
 // ---- dfx_tc.cu
 bool dfx_tc_supported(int d);

@@ -36,14 +36,14 @@ __global__ void __launch_bounds__(256)
 pq_rm_to_il_kernel(const int64_t* __restrict__ list_off, const int64_t* __restrict__ blk_off, int64_t nlist,
                    const uint8_t* __restrict__ codes, const float* __restrict__ tvals,
                    const int32_t* __restrict__ ids, uint8_t* __restrict__ il_codes, float* __restrict__ il_tvals,
-                   int32_t* __restrict__ il_ids) {
+                   int32_t* __restrict__ il_ids, int layout) {
     const int64_t blk = blockIdx.x;
     const int64_t l = il_list_of_block(blk_off, nlist, blk);
     const int64_t base = list_off[l] + (blk - blk_off[l]) * 32, end = list_off[l + 1];
     for (int e = threadIdx.x; e < 1024; e += 256) {
         const int v = e >> 5, m = e & 31;
         const int64_t i = base + v;
-        il_codes[blk * 1024 + dfx_il_byte(v, m)] = (i < end) ? codes[i * 32 + m] : (uint8_t)0;
+        il_codes[blk * 1024 + dfx_il_byte_of(layout, v, m)] = (i < end) ? codes[i * 32 + m] : (uint8_t)0;
     }
     if (threadIdx.x < 32) {
         const int64_t i = base + threadIdx.x;
@@ -56,14 +56,14 @@ __global__ void __launch_bounds__(256)
 pq_il_to_rm_kernel(const int64_t* __restrict__ list_off, const int64_t* __restrict__ blk_off, int64_t nlist,
                    const uint8_t* __restrict__ il_codes, const float* __restrict__ il_tvals,
                    const int32_t* __restrict__ il_ids, uint8_t* __restrict__ codes, float* __restrict__ tvals,
-                   int32_t* __restrict__ ids) {
+                   int32_t* __restrict__ ids, int layout) {
     const int64_t blk = blockIdx.x;
     const int64_t l = il_list_of_block(blk_off, nlist, blk);
     const int64_t base = list_off[l] + (blk - blk_off[l]) * 32, end = list_off[l + 1];
     for (int e = threadIdx.x; e < 1024; e += 256) {
         const int v = e >> 5, m = e & 31;
         const int64_t i = base + v;
-        if (i < end) codes[i * 32 + m] = il_codes[blk * 1024 + dfx_il_byte(v, m)];
+        if (i < end) codes[i * 32 + m] = il_codes[blk * 1024 + dfx_il_byte_of(layout, v, m)];
     }
     if (threadIdx.x < 32) {
         const int64_t i = base + threadIdx.x;
@@ -80,7 +80,12 @@ bool dfx_il_wanted(const dfx_index* idx) {
 
 // payload/tvals/ids (row-major, list-sorted) -> il_* ; frees the row-major arrays
 void dfx_pq_rm_to_il(dfx_index* idx, cudaStream_t st) {
-    if (idx->il || !dfx_il_wanted(idx)) return;
+    if (!dfx_il_wanted(idx)) return;
+    if (idx->il) {
+        if (idx->il_layout == idx->il_variant) return;
+        dfx_pq_il_to_rm(idx, st);  // other block layout requested: go through the row-major form
+    }
+    const int layout = idx->il_variant;
     const int64_t nlist = idx->cfg.nlist;
     std::vector<int64_t> h_blk((size_t)nlist + 1);
     h_blk[0] = 0;
@@ -96,13 +101,14 @@ void dfx_pq_rm_to_il(dfx_index* idx, cudaStream_t st) {
         DFX_LAUNCH(pq_rm_to_il_kernel, (unsigned)nblk, 256, 0, st, idx->list_off.as<int64_t>(),
                    idx->blk_off.as<int64_t>(), nlist, idx->payload.as<uint8_t>(), idx->tvals.as<float>(),
                    idx->ids.as<int32_t>(), idx->il_codes.as<uint8_t>(), idx->il_tvals.as<float>(),
-                   idx->il_ids.as<int32_t>());
+                   idx->il_ids.as<int32_t>(), layout);
     DFX_CUDA(cudaStreamSynchronize(st));  // h_blk is on the stack of this call
     idx->payload.release();
     idx->tvals.release();
     idx->ids.release();
     idx->nblk = nblk;
     idx->il = true;
+    idx->il_layout = layout;
     idx->inv_valid = false;
 }
 
@@ -117,13 +123,14 @@ void dfx_pq_il_to_rm(dfx_index* idx, cudaStream_t st) {
         DFX_LAUNCH(pq_il_to_rm_kernel, (unsigned)idx->nblk, 256, 0, st, idx->list_off.as<int64_t>(),
                    idx->blk_off.as<int64_t>(), idx->cfg.nlist, idx->il_codes.as<uint8_t>(),
                    idx->il_tvals.as<float>(), idx->il_ids.as<int32_t>(), idx->payload.as<uint8_t>(),
-                   idx->tvals.as<float>(), idx->ids.as<int32_t>());
+                   idx->tvals.as<float>(), idx->ids.as<int32_t>(), idx->il_layout);
     DFX_CUDA(cudaStreamSynchronize(st));
     idx->il_codes.release();
     idx->il_tvals.release();
     idx->il_ids.release();
     idx->nblk = 0;
     idx->il = false;
+    idx->il_layout = 0;
     idx->inv_valid = false;
 }
 

@@ -221,11 +221,17 @@ pq_prep_kernel(const float* __restrict__ Q, int d, int M, int ksub, int dsub,
             if (transposed) s_t[m * (ksub + 1) + (idx - m * ksub)] = -2.f * acc;
             else lut[q * tot + idx] = -2.f * acc;
         }
-        if (transposed) {  // M == 32 here
+        if (transposed == 1) {  // M == 32 here: [code][m]
             __syncthreads();
             for (int o = threadIdx.x; o < tot; o += blockDim.x) {
                 const int j = o >> 5, m = o & 31;
                 lut[q * tot + o] = s_t[m * (ksub + 1) + j];
+            }
+        } else if (transposed == 2) {  // M == 32, wide rows: [code][64], column c holds m = c & 31
+            __syncthreads();           // (scan_pq_il2_kernel reads column lane + t without a wrap)
+            for (int o = threadIdx.x; o < 2 * tot; o += blockDim.x) {
+                const int j = o >> 6, m = o & 31;
+                lut[q * 2 * tot + o] = s_t[m * (ksub + 1) + j];
             }
         }
     }
@@ -646,9 +652,9 @@ void dfx_search_impl(dfx_index* idx, int64_t nq, const float* d_x, int64_t k64, 
 
         if (kind == DFX_IVF_PQ) {
             const int M = idx->M, ksub = idx->ksub;
-            idx->w_lut.reserve((size_t)qc * M * ksub * 4);
+            const int il = idx->il ? idx->il_layout : 0;  // 0 row-major, 1 / 2 = block layout
+            idx->w_lut.reserve((size_t)qc * M * ksub * 4 * (il == 2 ? 2 : 1));
             idx->w_dis0.reserve((size_t)qc * nprobe * 4);
-            const int il = idx->il ? 1 : 0;
             const size_t prep_smem = (size_t)((d + 3) / 4) * 16 + (il ? (size_t)M * (ksub + 1) * 4 : 0);
             if (prep_smem > 48 * 1024)
                 DFX_CUDA(cudaFuncSetAttribute(pq_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -656,7 +662,9 @@ void dfx_search_impl(dfx_index* idx, int64_t nq, const float* d_x, int64_t k64, 
             DFX_LAUNCH(pq_prep_kernel, (unsigned)qc, 256, prep_smem, st, xq, d, M, ksub, idx->dsub,
                        idx->codebooks.as<float>(), idx->centroids.as<float>(), keys, nprobe,
                        idx->w_lut.as<float>(), idx->w_dis0.as<float>(), il);
-            if (il) {
+            if (il == 2) {
+                dfx_launch_scan_pq_il2(idx, qc, keys, nprobe, G, ngroups, k, cap, part, st);
+            } else if (il) {
                 dfx_launch_scan_pq_il(idx, qc, keys, nprobe, G, ngroups, k, cap, part, st);
             } else {
             const size_t smem = (size_t)M * ksub * 4 + (size_t)4 * cap * 8;

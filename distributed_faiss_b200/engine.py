@@ -34,7 +34,7 @@ EXPORTED_SYMBOLS = [
     "dfx_get_nprobe", "dfx_ntotal", "dfx_nlist", "dfx_is_trained", "dfx_get_centroids", "dfx_merge",
     "dfx_merge_dev", "dfx_map_ids_dev", "dfx_get_array", "dfx_set_array", "dfx_import_done",
     "dfx_last_stats", "dfx_profile_enable", "dfx_profile_read", "dfx_launch_count", "dfx_synth_init", "dfx_synth_rows_dev", "dfx_free",
-    "dfx_last_error", "dfx_version",
+    "dfx_last_error", "dfx_version", "dfx_debug_il_byte",
 ]
 
 

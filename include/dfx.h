@@ -71,7 +71,9 @@ int dfx_add_dev(dfx_index *idx, int64_t n, const float *d_x, void *stream);
  * "train_seed" (1234) -- the faiss Clustering defaults; "tensor_cores" (1): 0 forces the plain
  * fp32 FFMA coarse quantizer instead of the tcgen05 screening path (same results);
  * "interleaved" (1): 0 keeps IVF-PQ codes row-major and scans them one vector per lane
- * instead of the interleaved lane-per-subquantizer layout (same results) */
+ * instead of the interleaved lane-per-subquantizer layout (same results);
+ * "scan_variant" (1): 2 selects the experimental lane-per-vector block layout and scan kernel
+ * (dfx_scan_il2.cu; same results by construction, not yet validated on hardware) */
 int dfx_set_param(dfx_index *idx, const char *name, double value);
 /* pre-size the shard for n_total vectors (optional; avoids regrowth while bulk loading) */
 int dfx_reserve(dfx_index *idx, int64_t n_total);
@@ -163,6 +165,9 @@ int dfx_free(void *d_ptr);
 
 const char *dfx_last_error(void);
 const char *dfx_version(void);
+/* byte offset, inside a 1 KB block of 32 IVF-PQ vectors, of subquantizer m of vector v for block
+ * layout 1 or 2 (host function; lets the layout be checked without a GPU) */
+int dfx_debug_il_byte(int layout, int v, int m);
 
 #ifdef __cplusplus
 }

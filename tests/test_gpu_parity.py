@@ -403,3 +403,50 @@ def test_interleaved_and_row_major_pq_layouts_agree():
     g2.set_state(o.get_state())                      # import interleaves
     g2.nprobe = 6; o.nprobe = 6
     _assert_same(*g2.search(xq, 10), *o.search(xq, 10), "imported, interleaved")
+
+
+@pytest.mark.skipif(__import__("os").environ.get("DFX_EXPERIMENTAL") != "1",
+                    reason="scan_variant=2 has not been validated on hardware yet; run with DFX_EXPERIMENTAL=1")
+def test_scan_variant_2_matches_oracle():
+    """IVF-PQ, M=32, experimental lane-per-vector scan (dfx_scan_il2.cu): block layout 2, wide
+    table, register top-k (k <= 32) and the shared-memory fallback (k > 32) return the oracle's
+    bits; layout changes in both directions, incremental adds, export/import and reconstruct."""
+    from oracle import oracle as O
+
+    E = _engine()
+    rs = np.random.RandomState(21)
+    d, nlist, M, n = 128, 48, 32, 30_011
+    xb = clustered(rs, n, d, ncl=60)
+    xb[-500:] = xb[:500]                             # exact duplicates: ties decided by the id
+    xq = xb[:37] + 0.01 * rs.randn(37, d).astype(np.float32)
+    xq[:5] = xb[:5]
+    g = E.GpuIndex(E.KIND_IVF_PQ, d, L2, nlist=nlist, pq_m=M)
+    g.set_param("scan_variant", 2)
+    g.train(xb[:8000])
+    g.add(xb[:10_000]); g.nprobe = 6
+    g.search(xq, 10)                                 # builds layout 2
+    g.add(xb[10_000:])                               # incremental add on top of it
+    o = O.OracleIVFPQ(d, nlist, M, 8, coarse_metric=L2)
+    o.set_state(g.get_state())
+    assert o.ntotal == n
+    ids = np.array([0, 5, n - 1, -1, 12345], dtype=np.int64)
+    for nprobe, k in ((6, 10), (nlist, 32), (1, 1), (17, 7), (nlist, 100), (8, 300)):
+        g.nprobe = nprobe; o.nprobe = nprobe
+        Do, Io = o.search(xq, k)
+        g.set_param("scan_variant", 2)
+        _assert_same(*g.search(xq, k), Do, Io, f"variant 2 nprobe={nprobe} k={k}")
+        R2 = g.reconstruct_rows(ids)
+        g.set_param("scan_variant", 1)
+        _assert_same(*g.search(xq, k), Do, Io, f"variant 1 nprobe={nprobe} k={k}")
+        R1 = g.reconstruct_rows(ids)
+        assert np.array_equal(R1[[0, 1, 2, 4]], R2[[0, 1, 2, 4]]) and np.isnan(R2[3]).all()
+    g.set_param("scan_variant", 2)
+    for nq in (1, 3, 200):                           # one list per CTA at small batches
+        q = np.ascontiguousarray(np.tile(xq, (6, 1))[:nq])
+        g.nprobe = 9; o.nprobe = 9
+        _assert_same(*g.search(q, 10), *o.search(q, 10), f"variant 2 nq={nq}")
+    g2 = E.GpuIndex(E.KIND_IVF_PQ, d, L2, nlist=nlist, pq_m=M)
+    g2.set_param("scan_variant", 2)
+    g2.set_state(o.get_state())
+    g2.nprobe = 6; o.nprobe = 6
+    _assert_same(*g2.search(xq, 10), *o.search(xq, 10), "imported, variant 2")
