@@ -351,12 +351,14 @@ void dfx_launch_scan_pq_il2(dfx_index* idx, int64_t qc, const int32_t* keys, int
     if (reg) {
         auto kern = scan_pq_il2_kernel<true>;
         DFX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        DFX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));  // 3 CTAs/SM
         DFX_LAUNCH(kern, (unsigned)(qc * ngroups), IL2_THREADS, smem, st, idx->w_lut.as<float>(),
                    idx->w_dis0.as<float>(), keys, nprobe, G, ngroups, idx->blk_off.as<int64_t>(),
                    idx->il_codes.as<uint4>(), idx->il_tvals.as<float>(), idx->il_ids.as<int32_t>(), k, cap, part);
     } else {
         auto kern = scan_pq_il2_kernel<false>;
         DFX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        DFX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));  // 3 CTAs/SM
         DFX_LAUNCH(kern, (unsigned)(qc * ngroups), IL2_THREADS, smem, st, idx->w_lut.as<float>(),
                    idx->w_dis0.as<float>(), keys, nprobe, G, ngroups, idx->blk_off.as<int64_t>(),
                    idx->il_codes.as<uint4>(), idx->il_tvals.as<float>(), idx->il_ids.as<int32_t>(), k, cap, part);

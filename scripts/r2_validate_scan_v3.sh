@@ -1,0 +1,24 @@
+#!/bin/bash
+# First GPU call of round 2: validate and time the experimental lane-per-vector scan
+# (scan_variant=2, distributed_faiss_b200/csrc/dfx_scan_il2.cu).  Run from the repo root:
+#   gpurun --timeout 1500 -- 'bash scripts/r2_validate_scan_v3.sh'
+# Everything lands in gpurun_out/ (copy what is worth keeping into profiles/).
+set -u
+mkdir -p gpurun_out
+echo "== parity of variant 2 (and the rest of the suite with the default variant)"
+DFX_EXPERIMENTAL=1 timeout 600 python -m pytest tests -m gpu -q -x -k "scan_variant_2 or interleaved or ivf_matches" 2>&1 | tail -15 | tee gpurun_out/r2_v3_parity.log
+if ! grep -q " passed" gpurun_out/r2_v3_parity.log || grep -q "failed" gpurun_out/r2_v3_parity.log; then
+    echo "variant 2 is NOT green: stop here, read gpurun_out/r2_v3_parity.log"
+    exit 1
+fi
+echo "== whole gpu suite with variant 2 as the default layout of every new IVF-PQ index"
+DFX_SCAN_VARIANT=2 DFX_EXPERIMENTAL=1 timeout 900 python -m pytest tests -m gpu -q -x 2>&1 | tail -5 | tee gpurun_out/r2_v3_suite.log
+echo "== bench, default variant then variant 2 (same box, back to back)"
+timeout 600 python bench.py --steps 20 --warmup 3 > gpurun_out/r2_bench_v2.json 2> gpurun_out/r2_bench_v2.err
+tail -c 2000 gpurun_out/r2_bench_v2.json
+DFX_SCAN_VARIANT=2 timeout 600 python bench.py --steps 20 --warmup 3 > gpurun_out/r2_bench_v3.json 2> gpurun_out/r2_bench_v3.err
+tail -c 2000 gpurun_out/r2_bench_v3.json
+echo "== ncu: one full capture of the new scan kernel (bench.py opens the profiler window around the timed region)"
+DFX_SCAN_VARIANT=2 timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:scan_pq_il2 -c 2 \
+    -o gpurun_out/r2_scan_pq_il2 python bench.py --steps 1 --warmup 1 > gpurun_out/r2_ncu.log 2>&1
+tail -3 gpurun_out/r2_ncu.log
