@@ -35,6 +35,9 @@ from .index_state import IndexState
 logger = logging.getLogger("distributed_faiss_b200")
 
 INDEX_FILE = "index.dfx.npz"
+# the reference's file name (index.py:104); written instead of INDEX_FILE when the cfg carries
+# index_format="faiss", and read when no INDEX_FILE is present (see faiss_io.py)
+FAISS_INDEX_FILE = "index.faiss"
 
 
 def default_engine_factory(cfg: IndexCfg):
@@ -284,8 +287,15 @@ class Index:
                 return False
             index_file, meta_file, buffer_file, cfg_file = get_index_files(self.cfg.index_storage_dir)
             state = self.faiss_index.get_state()
-            tmp = index_file + ".tmp.npz"
-            np.savez(tmp, **{k: np.asarray(v) for k, v in state.items()})
+            if self.cfg.extra.get("index_format", "dfx") == "faiss":
+                from . import faiss_io
+
+                index_file = os.path.join(self.cfg.index_storage_dir, FAISS_INDEX_FILE)
+                tmp = index_file + ".tmp"
+                faiss_io.write_index(state, tmp, nprobe=int(getattr(self.faiss_index, "nprobe", 1)))
+            else:
+                tmp = index_file + ".tmp.npz"
+                np.savez(tmp, **{k: np.asarray(v) for k, v in state.items()})
             os.replace(tmp, index_file)
             with open(meta_file, "wb") as fh:
                 pickle.dump(self.id_to_metadata, fh)
@@ -309,7 +319,8 @@ class Index:
     def from_storage_dir(cls, index_storage_dir: str, cfg: IndexCfg = None, ignore_buffer: bool = True,
                          engine_factory: Optional[Callable] = None) -> Union[None, "Index"]:
         index_file, meta_file, buffer_file, cfg_file = get_index_files(index_storage_dir)
-        if not os.path.exists(index_file):
+        faiss_file = os.path.join(index_storage_dir, FAISS_INDEX_FILE)
+        if not os.path.exists(index_file) and not os.path.exists(faiss_file):
             return None
         if not os.path.exists(meta_file):
             raise RuntimeError("no meta file found. Can't use index.")
@@ -326,8 +337,13 @@ class Index:
         build_cfg = cfg
         if not cfg.index_builder_type and os.path.isfile(cfg_file):
             build_cfg = IndexCfg.from_json(cfg_file)
-        with np.load(index_file, allow_pickle=False) as z:
-            state = {k: (z[k].item() if z[k].ndim == 0 else z[k]) for k in z.files}
+        if os.path.exists(index_file):
+            with np.load(index_file, allow_pickle=False) as z:
+                state = {k: (z[k].item() if z[k].ndim == 0 else z[k]) for k in z.files}
+        else:  # a shard saved by the reference (faiss.write_index) or with index_format="faiss"
+            from . import faiss_io
+
+            state, _ = faiss_io.read_index(faiss_file)
         saved_nprobe = cfg.nprobe
         engine = result._engine_factory(build_cfg)
         cfg.nprobe = saved_nprobe
