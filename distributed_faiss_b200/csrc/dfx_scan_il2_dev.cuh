@@ -1,0 +1,291 @@
+// dfx_scan_il2_dev.cuh -- device code of dfx_scan_il2.cu (also compiled by the CPU emulator, tests/emu/).
+// K4 v3: inverted-list scan of PQ codes, one lane per vector, wide table.
+// EXPERIMENTAL (dfx_set_param "scan_variant" = 2, off by default): written against the ncu
+// profile of scan_pq_il_kernel (profiles/r01_scan_pq_il_1B_v9.ncu-rep), not yet timed.
+//
+// Replaces the inner loop of faiss IndexIVFPQ::search (reached from reference
+// distributed_faiss/index.py:257) -- `dis = dis0 + sum_m table[m][code[m]]` over every code of
+// every probed list; same canonical arithmetic as the other scan kernels (oracle pq_sum).
+//
+// What the profile of v2 said, and what changes here:
+//   * v2 is bound by the LSU data pipe (88 % of its wavefront peak): ~90 wavefronts per
+//     32-vector block, of which only 32 are the table lookups.  20 are the global loads -- each
+//     128-bit code load touched all eight 128-byte lines of the block (lanes 32 bytes apart) and
+//     moved every sector over the L2->L1 crossbar twice; ~27 are the shared-memory sorts of the
+//     per-warp candidate buffers; 7 are the butterfly shuffles.
+//   * Layout 2 (dfx_il2_byte): lane v owns vector v; the two 16-byte halves of all lanes are
+//     contiguous, so each 128-bit load of the warp is one 512-byte run (4 wavefronts).
+//   * One lane per vector needs no shuffles: lane v walks m = (t + v) & 31, t = 0..31.  The table
+//     rows are 64 floats wide (column c holds m = c & 31), so the lane reads column v + t with no
+//     wrap-around and the 32 lanes hit 32 different banks at every step.  The halving tree of
+//     oracle pq_sum joins, at each level, the residue classes of m modulo a power of two; a
+//     rotation of m maps classes to classes, so the tree over t joins the same sets (operands of
+//     a node possibly swapped: fp32 addition is commutative) -> bit-identical sums.
+//   * The shared-memory address of a lookup is ONE instruction: PRMT drops the code byte into
+//     byte 1 of (4 * lane), giving code * 256 + 4 * lane; the table base (uniform register) and
+//     4 * t (immediate) ride in the LDS address.  The tree is 15 packed FADD2 + 1 FADD.
+//     ~100 issued instructions per block instead of ~265.
+//   * k <= 32: the k best of a warp live in REGISTERS (lane i = i-th best, 64-bit composite);
+//     admitted candidates go to a 64-slot queue and are merged 32 at a time with a bitonic
+//     network over shuffles (42 SHFL per merge instead of a ~190-wavefront shared-memory sort).
+//     Ids are not streamed: the queue holds positions, ids are gathered when the queue is
+//     merged (one latency per merge) or on an exact tie with the k-th best.
+//   * The block stream of a warp runs across list boundaries with two blocks in flight, so a new
+//     list does not expose a DRAM latency (a warp owns only ~7 blocks of each list).
+#pragma once
+#include "dfx_internal.h"
+#include "dfx_topk.cuh"
+#include "dfx_ptx.cuh"
+
+constexpr int IL2_THREADS = 256;
+constexpr int IL2_NW = IL2_THREADS / 32;
+constexpr int IL2_LUT_BYTES = 256 * 64 * 4;  // wide table of one query
+constexpr int IL2_QCAP = 64;                 // queue slots per warp (register top-k path)
+constexpr int IL2_MAXG = 16;                 // probes per CTA (choose_group caps G at 16)
+
+// ascending bitonic sort of one 64-bit value per lane
+__device__ __forceinline__ uint64_t il2_sort32_asc(uint64_t x, int lane) {
+#pragma unroll
+    for (int size = 2; size <= 32; size <<= 1) {
+#pragma unroll
+        for (int stride = size >> 1; stride >= 1; stride >>= 1) {
+            const uint64_t o = __shfl_xor_sync(0xffffffffu, x, stride);
+            const bool up = (lane & size) == 0;  // size == 32: true for every lane
+            const bool lower = (lane & stride) == 0;
+            const uint64_t mn = x < o ? x : o, mx = x < o ? o : x;
+            x = (lower == up) ? mn : mx;
+        }
+    }
+    return x;
+}
+// kept, x_asc: ascending over lanes.  returns the 32 smallest of their union, ascending.
+// (element-wise min of an ascending and a descending sequence is bitonic and holds the 32
+// smallest; five half-cleaner stages sort it)
+__device__ __forceinline__ uint64_t il2_merge_sorted(uint64_t kept, uint64_t x_asc, int lane) {
+    const uint64_t xr = __shfl_sync(0xffffffffu, x_asc, 31 - lane);
+    uint64_t y = kept < xr ? kept : xr;
+#pragma unroll
+    for (int stride = 16; stride >= 1; stride >>= 1) {
+        const uint64_t o = __shfl_xor_sync(0xffffffffu, y, stride);
+        const bool lower = (lane & stride) == 0;
+        const uint64_t mn = y < o ? y : o, mx = y < o ? o : y;
+        y = lower ? mn : mx;
+    }
+    return y;
+}
+
+// Merge a warp's queue (cnt entries of key << 32 | position) into its register-resident set,
+// 32 entries at a time; the ids of the queued positions are gathered here.  Returns the new set
+// and, once k candidates are held, the k-th best (value, id), which is also folded into the
+// CTA-wide bound.  Everything travels by value so that the caller's state stays in registers.
+struct Il2Flushed {
+    uint64_t kept;
+    float thr;
+    uint32_t thr_sec;
+};
+__device__ __noinline__ Il2Flushed il2_flush(uint64_t kept, const uint64_t* queue, int cnt, int k,
+                                             const int32_t* __restrict__ il_ids, unsigned int* cta_key, float thr,
+                                             uint32_t thr_sec, int lane) {
+    for (int base = 0; base < cnt; base += 32) {
+        const int e = base + lane;
+        uint64_t x = DFX_COMP_NONE;
+        if (e < cnt) {
+            const uint64_t c = queue[e];
+            x = (c & 0xffffffff00000000ull) | (uint64_t)dfx_ld_nc_u(il_ids + (uint32_t)c);
+        }
+        kept = il2_merge_sorted(kept, il2_sort32_asc(x, lane), lane);
+    }
+    __syncwarp();  // queue fully read before later pushes overwrite it
+    const uint64_t kth = __shfl_sync(0xffffffffu, kept, k - 1);
+    if (kth != DFX_COMP_NONE) {
+        thr = dfx_key2f((uint32_t)(kth >> 32));
+        thr_sec = (uint32_t)kth;
+        if (lane == 0) atomicMin(cta_key, (unsigned int)(kth >> 32));
+    }
+    Il2Flushed r;
+    r.kept = kept;
+    r.thr = thr;
+    r.thr_sec = thr_sec;
+    return r;
+}
+
+// lutW: [nq][256][64] (wide transposed table, pq_prep_kernel mode 2)
+// REG: k <= 32, register-resident top-k;  !REG: WarpTopK buffers in shared memory (any k)
+template <bool REG>
+__global__ void __launch_bounds__(IL2_THREADS, 3)
+scan_pq_il2_kernel(const float* __restrict__ lutW, const float* __restrict__ dis0, const int32_t* __restrict__ keys,
+                   int nprobe, int G, int ngroups, const int64_t* __restrict__ blk_off,
+                   const uint4* __restrict__ il_codes, const float* __restrict__ il_tvals,
+                   const int32_t* __restrict__ il_ids, int k, int cap, uint64_t* __restrict__ part) {
+    DFX_DYN_SMEM(unsigned char, smem_raw, 128);
+    float* s_lut = reinterpret_cast<float*>(smem_raw);                      // [256][64]
+    uint64_t* s_buf = reinterpret_cast<uint64_t*>(smem_raw + IL2_LUT_BYTES);  // queues / WarpTopK buffers
+    __shared__ __align__(8) uint64_t s_lut_bar;
+    __shared__ unsigned int s_cta_key;  // CTA-wide admission bound (order-preserving key)
+    __shared__ int s_lb[IL2_MAXG], s_le[IL2_MAXG];  // first / end block of each probed list
+    __shared__ float s_ld0[IL2_MAXG];               // |q - c|^2 of each probed list
+
+    const int64_t q = blockIdx.x / ngroups;
+    const int g = blockIdx.x % ngroups;
+    const int tid = threadIdx.x, lane = tid & 31;
+    // through a shuffle so that the compiler knows `warp` (and with it the block cursor and the
+    // loop branches) is warp-uniform: the table base then stays in a uniform register and the
+    // lookups become LDS [R + UR + imm]
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    const int np = min(nprobe, (g + 1) * G) - g * G;  // probes of this CTA (<= IL2_MAXG)
+
+    if (tid == 0) {
+        s_cta_key = 0xff800000u;  // key of +inf: no bound yet
+        dfx_bulk_init(&s_lut_bar);
+    }
+    if (tid < np) {
+        const int l = keys[q * nprobe + g * G + tid];
+        s_lb[tid] = (l < 0) ? 0 : (int)blk_off[l];
+        s_le[tid] = (l < 0) ? 0 : (int)blk_off[l + 1];
+        s_ld0[tid] = dis0[q * nprobe + g * G + tid];
+    }
+    __syncthreads();
+    // the 64 KB table arrives by one bulk async copy (TMA engine)
+    if (tid == 0) dfx_bulk_issue(s_lut, lutW + q * (IL2_LUT_BYTES / 4), (uint32_t)IL2_LUT_BYTES, &s_lut_bar);
+
+    // ---- candidate set
+    WarpTopK wt;                                     // !REG
+    uint64_t kept = DFX_COMP_NONE;                   // REG: lane i = i-th best of this warp
+    uint64_t* queue = s_buf + (size_t)warp * IL2_QCAP;  // REG: (key << 32 | position)
+    int cnt = 0;
+    float thr = __int_as_float(0x7f800000);  // value of this warp's k-th best
+    uint32_t thr_sec = DFX_SEC_NONE;         // and its id
+    float bnd = __int_as_float(0x7f800000);  // register copy of the CTA bound (may lag: only looser)
+    if (!REG) wt.init(s_buf + (size_t)warp * cap, cap, k, &s_cta_key);
+
+    // merge the queue into `kept` (out of line: rare, and called from three places)
+    auto flush = [&]() {
+        const Il2Flushed f = il2_flush(kept, queue, cnt, k, il_ids, &s_cta_key, thr, thr_sec, lane);
+        kept = f.kept;
+        thr = f.thr;
+        thr_sec = f.thr_sec;
+        cnt = 0;
+    };
+
+    dfx_bulk_wait(&s_lut_bar);
+
+    const uint32_t lut_base = dfx_smem_addr(s_lut);
+    const uint32_t cu = (uint32_t)lane * 4u;  // byte offset of column `lane`; byte 1 receives the code
+
+    // one 32-vector block: lane = vector.  32 lookups (column lane + t of row code_t), the
+    // halving tree, then the admission test.
+    auto process = [&](const uint4& ca, const uint4& cb, float tv, float d0, int pos) {
+        const uint32_t w[8] = {ca.x, ca.y, ca.z, ca.w, cb.x, cb.y, cb.z, cb.w};
+        float y[32];
+#pragma unroll
+        for (int t = 0; t < 32; t++) {
+            // byte t&3 of word t>>2 -> byte 1 of (4 * lane): code * 256 + 4 * lane (one PRMT);
+            // table base + 4 * t fold into the LDS address (uniform register + immediate)
+            const uint32_t r = __byte_perm(w[t >> 2], cu, 0x6504u | ((uint32_t)(t & 3) << 4));
+            y[t] = dfx_lds_f32(r + lut_base + 4u * (uint32_t)t);
+        }
+        // tree levels 16, 8, 4, 2 on pairs (y[2i], y[2i+1]); level 1 joins the two halves
+        dfx_f32x2 p2[16];
+#pragma unroll
+        for (int i = 0; i < 16; i++) p2[i] = dfx_pack2(y[2 * i], y[2 * i + 1]);
+#pragma unroll
+        for (int off = 8; off >= 1; off >>= 1) {
+#pragma unroll
+            for (int i = 0; i < off; i++) p2[i] = dfx_add2(p2[i], p2[i + off]);
+        }
+        float s0, s1;
+        dfx_unpack2(p2[0], s0, s1);
+        const float v = d0 + (tv + (s0 + s1));  // padding has tv = +inf
+
+        if (REG) {
+            bool pass = v <= bnd;
+            if (__any_sync(0xffffffffu, pass)) {
+                bnd = dfx_key2f(*reinterpret_cast<volatile unsigned int*>(&s_cta_key));
+                pass = v <= bnd;  // equal to the bound: still admitted (rank decided by the id)
+                bool want = false;
+                if (pass) {
+                    if (v < thr) want = true;
+                    else if (v == thr) want = dfx_ld_nc_u(il_ids + (int64_t)pos * 32 + lane) < thr_sec;
+                }
+                const unsigned mask = __ballot_sync(0xffffffffu, want);
+                if (mask) {
+                    if (want)
+                        queue[cnt + __popc(mask & ((1u << lane) - 1u))] =
+                            ((uint64_t)dfx_f2key(v) << 32) | (uint64_t)((uint32_t)pos * 32u + (uint32_t)lane);
+                    cnt += __popc(mask);
+                    __syncwarp();
+                    if (cnt > IL2_QCAP - 32) flush();
+                }
+            }
+        } else {
+            uint32_t sec = 0;
+            const bool want = (v + 0.0f <= wt.cta_bound()) &&
+                              wt.admits(v, [&] { return dfx_ld_nc_u(il_ids + (int64_t)pos * 32 + lane); }, sec);
+            wt.push_lanes(want, v, sec);
+        }
+    };
+
+    // ---- the warp's block stream: blocks lb + warp, + NW, ... of each probed list, in probe order
+    int cur_p = -1, cur_b = 0, cur_e = 0;
+    float cur_d0 = 0.f;
+    auto next_block = [&]() -> bool {
+        cur_b += IL2_NW;
+        while (cur_b >= cur_e) {
+            if (++cur_p >= np) {
+                cur_p = np;
+                return false;
+            }
+            cur_b = s_lb[cur_p] + warp;
+            cur_e = s_le[cur_p];
+            cur_d0 = s_ld0[cur_p];
+        }
+        return true;
+    };
+#define IL2_FETCH(A, B, T, D0, POS)                                          \
+    do {                                                                     \
+        if (next_block()) {                                                  \
+            const uint4* pc_ = il_codes + (int64_t)cur_b * 64 + lane;        \
+            A = dfx_ld_stream(pc_);                                          \
+            B = dfx_ld_stream(pc_ + 32);                                     \
+            T = dfx_ld_stream_f(il_tvals + (int64_t)cur_b * 32 + lane);      \
+            D0 = cur_d0;                                                     \
+            POS = cur_b;                                                     \
+        } else {                                                             \
+            POS = -1;                                                        \
+        }                                                                    \
+    } while (0)
+
+    uint4 a0 = {}, b0 = {}, a1 = {}, b1 = {}, a2 = {}, b2 = {};
+    float t0 = 0.f, t1 = 0.f, t2 = 0.f, e0 = 0.f, e1 = 0.f, e2 = 0.f;
+    int p0, p1, p2;
+    IL2_FETCH(a0, b0, t0, e0, p0);
+    IL2_FETCH(a1, b1, t1, e1, p1);
+    for (;;) {  // two blocks in flight while one is processed
+        IL2_FETCH(a2, b2, t2, e2, p2);
+        if (p0 < 0) break;
+        process(a0, b0, t0, e0, p0);
+        IL2_FETCH(a0, b0, t0, e0, p0);
+        if (p1 < 0) break;
+        process(a1, b1, t1, e1, p1);
+        IL2_FETCH(a1, b1, t1, e1, p1);
+        if (p2 < 0) break;
+        process(a2, b2, t2, e2, p2);
+    }
+#undef IL2_FETCH
+
+    uint64_t* out = part + ((int64_t)q * ngroups + g) * k;
+    if (REG) {
+        if (cnt > 0) flush();
+        __syncthreads();  // every warp is done with its queue: the area is reused for the merge
+        s_buf[warp * 32 + lane] = kept;
+        __syncthreads();
+        if (warp == 0) {
+#pragma unroll 1
+            for (int w2 = 1; w2 < IL2_NW; w2++) kept = il2_merge_sorted(kept, s_buf[w2 * 32 + lane], lane);
+            if (lane < k) out[lane] = kept;
+        }
+    } else {
+        cta_merge_and_write<IL2_THREADS>(wt, s_buf, cap, k, out);
+    }
+}
+

@@ -185,78 +185,7 @@ void dfx_launch_select_comp(const uint64_t* comp, int64_t nrows, int n, int64_t 
     dfx_launch_select<256>(ldr, wr, nrows, n, k, st);
 }
 
-// =====================================================================================
-// K3: pq_prep.  lut[q][m][j] = -2 * ip_seq(q_m, P[m][j]);  dis0[q][p] = warp-dot ||q - c||^2
-// =====================================================================================
-// transposed != 0 (M == 32): the table is written as lut[q][j][m] for the lane-per-subquantizer
-// scan (dfx_scan_il.cu); it is staged through padded shared memory so both the codebook reads
-// and the global writes stay coalesced.
-__global__ void __launch_bounds__(256)
-pq_prep_kernel(const float* __restrict__ Q, int d, int M, int ksub, int dsub,
-               const float* __restrict__ codebooks, const float* __restrict__ cent,
-               const int32_t* __restrict__ keys, int nprobe, float* __restrict__ lut,
-               float* __restrict__ dis0, int transposed) {
-    extern __shared__ float s_q[];
-    float* s_t = s_q + ((d + 3) / 4) * 4;  // transposed mode: [M][ksub + 1]
-    const int64_t q = blockIdx.x;
-    for (int i = threadIdx.x; i < d; i += blockDim.x) s_q[i] = Q[q * d + i];
-    __syncthreads();
-    if (lut) {
-        const int tot = M * ksub;
-#pragma unroll 4
-        for (int idx = threadIdx.x; idx < tot; idx += blockDim.x) {
-            const int m = (ksub == 256) ? (idx >> 8) : (idx / ksub);
-            const float* p = codebooks + (size_t)idx * dsub;
-            const float* qm = s_q + m * dsub;
-            float acc = 0.f;
-            if (dsub == 4) {  // same seq-k order, one 16-byte load
-                const float4 pv = __ldg(reinterpret_cast<const float4*>(p));
-                acc = __fmaf_rn(qm[0], pv.x, acc);
-                acc = __fmaf_rn(qm[1], pv.y, acc);
-                acc = __fmaf_rn(qm[2], pv.z, acc);
-                acc = __fmaf_rn(qm[3], pv.w, acc);
-            } else {
-                for (int t = 0; t < dsub; t++) acc = __fmaf_rn(qm[t], p[t], acc);
-            }
-            if (transposed) s_t[m * (ksub + 1) + (idx - m * ksub)] = -2.f * acc;
-            else lut[q * tot + idx] = -2.f * acc;
-        }
-        if (transposed == 1) {  // M == 32 here: [code][m]
-            __syncthreads();
-            for (int o = threadIdx.x; o < tot; o += blockDim.x) {
-                const int j = o >> 5, m = o & 31;
-                lut[q * tot + o] = s_t[m * (ksub + 1) + j];
-            }
-        } else if (transposed == 2) {  // M == 32, wide rows: [code][64], column c holds m = c & 31
-            __syncthreads();           // (scan_pq_il2_kernel reads column lane + t without a wrap)
-            for (int o = threadIdx.x; o < 2 * tot; o += blockDim.x) {
-                const int j = o >> 6, m = o & 31;
-                lut[q * 2 * tot + o] = s_t[m * (ksub + 1) + j];
-            }
-        }
-    }
-    if (dis0) {
-        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-        for (int p = warp; p < nprobe; p += nw) {
-            int l = keys[q * nprobe + p];
-            float acc = 0.f;
-            if (l >= 0) {
-                const float* c = cent + (size_t)l * d;
-                for (int base = 4 * lane; base < d; base += 128) {
-                    float4 cv = *reinterpret_cast<const float4*>(c + base);
-                    float4 qv = *reinterpret_cast<const float4*>(s_q + base);
-                    float df;
-                    df = qv.x - cv.x; acc = __fmaf_rn(df, df, acc);
-                    df = qv.y - cv.y; acc = __fmaf_rn(df, df, acc);
-                    df = qv.z - cv.z; acc = __fmaf_rn(df, df, acc);
-                    df = qv.w - cv.w; acc = __fmaf_rn(df, df, acc);
-                }
-            }
-            acc = dfx_warp_butterfly(acc);
-            if (lane == 0) dis0[q * nprobe + p] = acc;
-        }
-    }
-}
+#include "dfx_pq_prep_dev.cuh"
 
 // =====================================================================================
 // K4: scan_pq.  one CTA = (query, group of G consecutive probes).  lane-per-vector:

@@ -32,6 +32,7 @@ __device__ __forceinline__ void dfx_block_bitonic_sort(uint64_t* s, int P) {
     __syncthreads();
 }
 
+#ifndef DFX_EMU  // the row-selection kernel and its launcher are not part of the CPU emulator build
 // Loader:  __device__ uint64_t operator()(int64_t row, int e) const   (DFX_COMP_NONE = no candidate)
 // Writer:  __device__ void operator()(int64_t row, int j, uint64_t comp) const   (j in [0,k))
 // dynamic smem: P * 8 bytes with P = pow2 >= max(k, min(n, sort_cap))
@@ -148,3 +149,4 @@ static inline void dfx_launch_select(Loader ld, Writer wr, int64_t nrows, int n,
     auto kern = dfx_select_rows_kernel<THREADS, Loader, Writer>;
     DFX_LAUNCH(kern, (unsigned)nrows, THREADS, smem, st, ld, wr, n, k, P, sort_cap);
 }
+#endif

@@ -1,0 +1,183 @@
+// simt.h -- a tiny SIMT runtime for the CPU emulator: one CTA at a time, every CUDA thread is a
+// ucontext fiber on ONE OS thread; fibers run until they reach a collective (warp exchange,
+// ballot, __syncwarp, __syncthreads) or an explicit yield, where the next fiber is scheduled.
+// Collectives are full-warp (all 32 lanes must arrive), which is how the scan kernels use them.
+// Dynamic shared memory is filled with a poison pattern before each CTA; shared-memory reads by
+// address are bounds-checked.  Test infrastructure only.
+#pragma once
+#include <stdint.h>
+#include <string.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <ucontext.h>
+#include <functional>
+#include <vector>
+
+namespace simt {
+
+struct Tid { unsigned x, y, z; };
+struct Fiber {
+    ucontext_t ctx;
+    Tid tid;
+    bool done;
+};
+struct Warp {
+    int arrive, gen;
+    uint64_t slot[32];
+};
+struct State {
+    std::vector<Fiber> fibers;
+    std::vector<char> stacks;
+    std::vector<Warp> warps;
+    int nthreads = 0, cur = -1;
+    int bar_arrive = 0, bar_gen = 0;
+    ucontext_t sched;
+    std::vector<unsigned char> dyn;
+    std::function<void()> kernel;
+    uint64_t rng = 0;  // != 0: fibers are resumed in a pseudo-random order
+    long switches = 0;
+    long events = 0;  // barrier completions + thread exits (deadlock watchdog)
+};
+inline State& S() {
+    static State s;
+    return s;
+}
+inline Tid g_block, g_bdim, g_gdim;
+
+inline Tid& cur_tid() { return S().fibers[S().cur].tid; }
+inline unsigned lane() { return (unsigned)S().cur & 31u; }
+inline unsigned char* dyn_smem() { return S().dyn.data(); }
+inline uint32_t smem_addr(const void* p) {
+    const unsigned char* c = static_cast<const unsigned char*>(p);
+    if (c < S().dyn.data() || c >= S().dyn.data() + S().dyn.size()) return 0xdead0000u;  // static __shared__: opaque
+    return (uint32_t)(c - S().dyn.data());
+}
+inline unsigned char* smem_ptr(uint32_t addr) {
+    if ((size_t)addr + 4 > S().dyn.size()) {
+        fprintf(stderr, "simt: shared-memory access at %u outside the %zu dynamic bytes (thread %d)\n", addr,
+                S().dyn.size(), S().cur);
+        abort();
+    }
+    return S().dyn.data() + addr;
+}
+inline void yield() {
+    S().switches++;
+    swapcontext(&S().fibers[S().cur].ctx, &S().sched);
+}
+inline void warp_barrier() {
+    Warp& w = S().warps[S().cur >> 5];
+    const int g = w.gen;
+    if (++w.arrive == 32) {
+        w.arrive = 0;
+        w.gen++;
+        S().events++;
+    } else {
+        while (w.gen == g) yield();
+    }
+}
+inline void cta_barrier() {
+    State& s = S();
+    const int g = s.bar_gen;
+    if (++s.bar_arrive == s.nthreads) {
+        s.bar_arrive = 0;
+        s.bar_gen++;
+        s.events++;
+    } else {
+        while (s.bar_gen == g) yield();
+    }
+}
+// every lane deposits v; returns the value deposited by lane `src`
+template <class T>
+inline T warp_exchange(T v, unsigned src) {
+    static_assert(sizeof(T) <= 8, "warp_exchange: at most 64 bits");
+    Warp& w = S().warps[S().cur >> 5];
+    uint64_t raw = 0;
+    memcpy(&raw, &v, sizeof(T));
+    w.slot[lane()] = raw;
+    warp_barrier();
+    const uint64_t got = w.slot[src];
+    warp_barrier();  // everyone has read before the slots are reused
+    T out;
+    memcpy(&out, &got, sizeof(T));
+    return out;
+}
+inline unsigned warp_ballot(bool pred) {
+    Warp& w = S().warps[S().cur >> 5];
+    w.slot[lane()] = pred ? 1 : 0;
+    warp_barrier();
+    unsigned m = 0;
+    for (int i = 0; i < 32; i++) m |= (unsigned)(w.slot[i] & 1) << i;
+    warp_barrier();
+    return m;
+}
+
+inline void fiber_entry() {
+    State& s = S();
+    s.kernel();
+    s.fibers[s.cur].done = true;
+    swapcontext(&s.fibers[s.cur].ctx, &s.sched);
+}
+
+// run `kernel` (a closure over the kernel arguments) on grid x block threads, dyn_bytes of
+// dynamic shared memory per CTA.  CTAs run one after the other.
+inline void launch(unsigned grid, unsigned block, size_t dyn_bytes, std::function<void()> kernel, uint64_t seed = 0) {
+    State& s = S();
+    if (block % 32 != 0 || block == 0 || block > 1024) {
+        fprintf(stderr, "simt: block size %u must be a multiple of 32\n", block);
+        abort();
+    }
+    constexpr size_t STACK = 512 * 1024;
+    s.kernel = kernel;
+    s.nthreads = (int)block;
+    s.rng = seed;
+    g_bdim = {block, 1, 1};
+    g_gdim = {grid, 1, 1};
+    s.stacks.resize((size_t)block * STACK);
+    for (unsigned b = 0; b < grid; b++) {
+        g_block = {b, 0, 0};
+        s.dyn.assign(dyn_bytes + 16, 0xCD);  // poison: reads of unwritten shared memory show up as garbage
+        s.dyn.resize(dyn_bytes);
+        s.fibers.assign(block, Fiber());
+        s.warps.assign(block / 32, Warp());
+        for (auto& w : s.warps) w.arrive = w.gen = 0;
+        s.bar_arrive = 0;
+        s.bar_gen = 0;
+        for (unsigned t = 0; t < block; t++) {
+            Fiber& f = s.fibers[t];
+            f.tid = {t, 0, 0};
+            f.done = false;
+            getcontext(&f.ctx);
+            f.ctx.uc_stack.ss_sp = s.stacks.data() + (size_t)t * STACK;
+            f.ctx.uc_stack.ss_size = STACK;
+            f.ctx.uc_link = nullptr;
+            makecontext(&f.ctx, fiber_entry, 0);
+        }
+        int live = (int)block;
+        long stale_sweeps = 0;
+        while (live > 0) {
+            const long before = s.events;
+            for (unsigned i = 0; i < block; i++) {
+                unsigned t = i;
+                if (s.rng) {  // xorshift: visit threads in a scrambled order
+                    s.rng ^= s.rng << 13; s.rng ^= s.rng >> 7; s.rng ^= s.rng << 17;
+                    t = (unsigned)(s.rng % block);
+                }
+                if (s.fibers[t].done) continue;
+                s.cur = (int)t;
+                swapcontext(&s.sched, &s.fibers[t].ctx);
+                if (s.fibers[t].done) {
+                    live--;
+                    s.events++;
+                }
+            }
+            stale_sweeps = (s.events == before) ? stale_sweeps + 1 : 0;
+            if (stale_sweeps > 100000) {
+                fprintf(stderr, "simt: CTA %u makes no progress (a collective some threads never reach?)\n", b);
+                abort();
+            }
+        }
+        s.cur = -1;
+    }
+}
+
+}  // namespace simt
