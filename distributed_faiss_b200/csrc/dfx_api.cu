@@ -80,6 +80,8 @@ int dfx_create(const dfx_cfg* cfg, dfx_index** out) {
         // experiments: DFX_SCAN_VARIANT=2 makes new indexes start on the lane-per-vector scan
         if (const char* e = getenv("DFX_SCAN_VARIANT"))
             if (atoi(e) == 2) idx->il_variant = 2;
+        if (const char* e = getenv("DFX_PREP_VARIANT"))
+            if (atoi(e) == 2) idx->prep_variant = 2;
     }
     DeviceGuard g(cfg->device);
     DFX_CUDA(cudaStreamCreateWithFlags(&idx->stream, cudaStreamNonBlocking));
@@ -117,6 +119,10 @@ int dfx_set_param(dfx_index* idx, const char* name, double value) {
         idx->il_enabled = value != 0;
         if (!idx->il_enabled) dfx_pq_il_to_rm(idx, idx->stream);
         else if (idx->trained && idx->n_pending == 0 && idx->n_sorted > 0) dfx_pq_rm_to_il(idx, idx->stream);
+    }
+    else if (n == "prep_variant") {
+        DFX_REQUIRE(value == 1 || value == 2, "prep_variant must be 1 or 2");
+        idx->prep_variant = (int)value;
     }
     else if (n == "scan_variant") {
         // 1 = scan_pq_il_kernel (8 lanes per vector), 2 = scan_pq_il2_kernel (lane per vector,
@@ -412,6 +418,7 @@ int dfx_set_array(dfx_index* idx, const char* name, const void* in, int64_t nbyt
     } else if (n == "codebooks" && idx->cfg.kind == DFX_IVF_PQ) {
         DFX_REQUIRE(nbytes == (int64_t)idx->M * idx->ksub * idx->dsub * 4, "codebooks: wrong size");
         upload(idx->codebooks, nbytes);
+        idx->cbT_valid = false;
     } else if (n == "list_off" && idx->is_ivf()) {
         DFX_REQUIRE(nbytes == (nlist + 1) * 8, "list_off: wrong size");
         upload(idx->list_off, nbytes);

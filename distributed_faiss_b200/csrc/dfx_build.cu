@@ -347,6 +347,7 @@ void dfx_train_impl(dfx_index* idx, int64_t n, const float* d_x, cudaStream_t st
         DFX_LAUNCH(residual_kernel, blocks_for(ns * d, 256), 256, 0, st, xt, idx->centroids.as<float>(),
                    d_assign.as<int32_t>(), ns, d, d_res.as<float>());
         idx->codebooks.reserve((size_t)M * ksub * dsub * 4);
+        idx->cbT_valid = false;
         for (int m = 0; m < M; m++) {
             DFX_LAUNCH(gather_rows_kernel, blocks_for(ns * dsub, 256), 256, 0, st, d_res.as<float>(),
                        (const int32_t*)nullptr, ns, dsub, m * dsub, d, d_subv.as<float>());

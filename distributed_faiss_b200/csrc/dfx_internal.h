@@ -42,6 +42,10 @@ struct dfx_index {
     int64_t nblk = 0;
     // which block layout / scan kernel: 1 = dfx_il_byte + scan_pq_il_kernel (default),
     // 2 = dfx_il2_byte + scan_pq_il2_kernel (dfx_scan_il2.cu; dfx_set_param "scan_variant")
+    // K3 variant (dfx_set_param "prep_variant"): 2 = pq_prep2_kernel on the transposed codebook
+    int prep_variant = 1;
+    DevBuf codebooksT;  // [ksub][M][dsub], built on demand
+    bool cbT_valid = false;
     int il_variant = 1;  // requested
     int il_layout = 0;   // layout the il_* arrays currently hold (valid while `il`)
 

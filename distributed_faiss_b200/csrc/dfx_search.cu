@@ -588,6 +588,20 @@ void dfx_search_impl(dfx_index* idx, int64_t nq, const float* d_x, int64_t k64, 
             if (prep_smem > 48 * 1024)
                 DFX_CUDA(cudaFuncSetAttribute(pq_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                               (int)prep_smem));
+            if (idx->prep_variant == 2 && il && M == 32 && ksub == 256 && idx->dsub == 4) {
+                // experimental K3: tables produced in output order from the transposed codebook,
+                // 8 queries per CTA (dfx_pq_prep_dev.cuh)
+                if (!idx->cbT_valid) {
+                    idx->codebooksT.reserve((size_t)M * ksub * idx->dsub * 4);
+                    DFX_LAUNCH(cb_transpose_kernel, (unsigned)((M * ksub * idx->dsub + 255) / 256), 256, 0, st,
+                               idx->codebooks.as<float>(), M, ksub, idx->dsub, idx->codebooksT.as<float>());
+                    idx->cbT_valid = true;
+                }
+                constexpr int QB = 8;
+                DFX_LAUNCH(pq_prep2_kernel<QB>, (unsigned)((qc + QB - 1) / QB), 256, (size_t)QB * d * 4, st, xq,
+                           qc, d, idx->codebooksT.as<float>(), idx->centroids.as<float>(), keys, nprobe,
+                           idx->w_lut.as<float>(), idx->w_dis0.as<float>(), il == 2 ? 1 : 0);
+            } else
             DFX_LAUNCH(pq_prep_kernel, (unsigned)qc, 256, prep_smem, st, xq, d, M, ksub, idx->dsub,
                        idx->codebooks.as<float>(), idx->centroids.as<float>(), keys, nprobe,
                        idx->w_lut.as<float>(), idx->w_dis0.as<float>(), il);

@@ -18,6 +18,8 @@ timeout 600 python bench.py --steps 20 --warmup 3 > gpurun_out/r2_bench_v2.json 
 tail -c 2000 gpurun_out/r2_bench_v2.json
 DFX_SCAN_VARIANT=2 timeout 600 python bench.py --steps 20 --warmup 3 > gpurun_out/r2_bench_v3.json 2> gpurun_out/r2_bench_v3.err
 tail -c 2000 gpurun_out/r2_bench_v3.json
+DFX_SCAN_VARIANT=2 DFX_PREP_VARIANT=2 timeout 600 python bench.py --steps 20 --warmup 3 > gpurun_out/r2_bench_v3_prep2.json 2> gpurun_out/r2_bench_v3_prep2.err
+tail -c 2000 gpurun_out/r2_bench_v3_prep2.json
 echo "== ncu: one full capture of the new scan kernel (bench.py opens the profiler window around the timed region)"
 DFX_SCAN_VARIANT=2 timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:scan_pq_il2 -c 2 \
     -o gpurun_out/r2_scan_pq_il2 python bench.py --steps 1 --warmup 1 > gpurun_out/r2_ncu.log 2>&1

@@ -46,6 +46,19 @@ int emu_pq_prep(const float* Q, int64_t nq, int d, int M, int ksub, int dsub, co
     return 0;
 }
 
+// experimental K3 variant 2: transposed codebook + QB = 8 queries per CTA
+int emu_pq_prep2(const float* Q, int64_t nq, int d, const float* codebooks, const float* cent, const int32_t* keys,
+                 int nprobe, float* lut, float* dis0, int wide) {
+    std::vector<float> cbT((size_t)32 * 256 * 4);
+    float* pT = cbT.data();
+    simt::launch((32 * 256 * 4 + 255) / 256, 256, 0, [=] { cb_transpose_kernel(codebooks, 32, 256, 4, pT); }, g_seed);
+    constexpr int QB = 8;
+    simt::launch((unsigned)((nq + QB - 1) / QB), 256, (size_t)QB * d * 4, [=] {
+        pq_prep2_kernel<QB>(Q, nq, d, pT, cent, keys, nprobe, lut, dis0, wide);
+    }, g_seed);
+    return 0;
+}
+
 int emu_scan_v2(const float* lutT, const float* dis0, const int32_t* keys, int64_t nq, int nprobe, int G, int ngroups,
                 const int64_t* blk_off, const uint8_t* il_codes, const float* il_tvals, const int32_t* il_ids, int k,
                 int cap, uint64_t* part) {

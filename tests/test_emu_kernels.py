@@ -183,6 +183,23 @@ def test_pq_prep_tables_and_dis0(emu, built, layout):
             assert dis0[q, j] == np.float32(O.warp_dot(xq[q], ix.centroids[l], 1))
 
 
+@pytest.mark.parametrize("layout", [1, 2])
+@pytest.mark.parametrize("nq", [1, 8, 13])
+def test_pq_prep_variant_2_equals_variant_1(emu, built, layout, nq):
+    """experimental K3 (transposed codebook, 8 queries per CTA) writes the same bits"""
+    ix, x, rs = built
+    p = Pipeline(emu, ix, layout, seed=nq)
+    xq = np.ascontiguousarray(x[100:100 + nq] + 0.1 * rs.randn(nq, 128).astype(np.float32))
+    keys, lut, dis0 = p.prep(xq, 5)
+    lut2 = np.full_like(lut, np.nan)
+    dis2 = np.full_like(dis0, np.nan)
+    cb = np.ascontiguousarray(p.st["codebooks"], dtype=np.float32)
+    cent = np.ascontiguousarray(p.st["centroids"], dtype=np.float32)
+    emu.emu_pq_prep2(_p(xq), C.c_int64(nq), 128, _p(cb), _p(cent), _p(keys), 5, _p(lut2), _p(dis2),
+                     1 if layout == 2 else 0)
+    assert lut2.tobytes() == lut.tobytes() and dis2.tobytes() == dis0.tobytes()
+
+
 CASES = [  # layout, k, nprobe, G, scheduler seed
     (1, 10, 4, 4, 0), (1, 10, 4, 1, 7),                   # shipping kernel: validates the emulator itself
     (2, 10, 4, 4, 0), (2, 10, 4, 1, 7), (2, 1, 3, 2, 3), (2, 32, 8, 8, 11),   # v3, register top-k

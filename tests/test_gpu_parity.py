@@ -450,3 +450,9 @@ def test_scan_variant_2_matches_oracle():
     g2.set_state(o.get_state())
     g2.nprobe = 6; o.nprobe = 6
     _assert_same(*g2.search(xq, 10), *o.search(xq, 10), "imported, variant 2")
+    # experimental K3 (prep_variant 2: transposed codebook, 8 queries per CTA) under both scans
+    g2.set_param("prep_variant", 2)
+    for variant in (2, 1):
+        g2.set_param("scan_variant", variant)
+        for nq in (1, 13, 37):
+            _assert_same(*g2.search(xq[:nq], 10), *o.search(xq[:nq], 10), f"prep 2, scan {variant}, nq={nq}")
