@@ -26,8 +26,9 @@
 //     4 * t (immediate) ride in the LDS address.  The tree is 15 packed FADD2 + 1 FADD.
 //     ~100 issued instructions per block instead of ~265.
 //   * k <= 32: the k best of a warp live in REGISTERS (lane i = i-th best, 64-bit composite);
-//     admitted candidates go to a 64-slot queue and are merged 32 at a time with a bitonic
-//     network over shuffles (42 SHFL per merge instead of a ~190-wavefront shared-memory sort).
+//     admitted candidates go to a 64-slot queue; whenever 32 are queued they are merged with a
+//     bitonic network over shuffles (42 SHFL per merge instead of a ~190-wavefront shared-memory
+//     sort), the remainder stays queued.
 //     Ids are not streamed: the queue holds positions, ids are gathered when the queue is
 //     merged (one latency per merge) or on an exact tie with the k-th best.
 //   * The block stream of a warp runs across list boundaries with two blocks in flight, so a new
@@ -74,28 +75,32 @@ __device__ __forceinline__ uint64_t il2_merge_sorted(uint64_t kept, uint64_t x_a
     return y;
 }
 
-// Merge a warp's queue (cnt entries of key << 32 | position) into its register-resident set,
-// 32 entries at a time; the ids of the queued positions are gathered here.  Returns the new set
-// and, once k candidates are held, the k-th best (value, id), which is also folded into the
-// CTA-wide bound.  Everything travels by value so that the caller's state stays in registers.
+// Merge the first min(cnt, 32) entries of a warp's queue (key << 32 | position) into its
+// register-resident set and move the rest to the front of the queue; the ids of the merged
+// positions are gathered here.  Returns the new set, the new count and, once k candidates are held,
+// the k-th best (value, id), which is also folded into the CTA-wide bound.  Everything travels by
+// value so that the caller's state stays in registers.
 struct Il2Flushed {
     uint64_t kept;
     float thr;
     uint32_t thr_sec;
+    int cnt;
 };
-__device__ __noinline__ Il2Flushed il2_flush(uint64_t kept, const uint64_t* queue, int cnt, int k,
+__device__ __noinline__ Il2Flushed il2_flush(uint64_t kept, uint64_t* queue, int cnt, int k,
                                              const int32_t* __restrict__ il_ids, unsigned int* cta_key, float thr,
                                              uint32_t thr_sec, int lane) {
-    for (int base = 0; base < cnt; base += 32) {
-        const int e = base + lane;
-        uint64_t x = DFX_COMP_NONE;
-        if (e < cnt) {
-            const uint64_t c = queue[e];
-            x = (c & 0xffffffff00000000ull) | (uint64_t)dfx_ld_nc_u(il_ids + (uint32_t)c);
-        }
-        kept = il2_merge_sorted(kept, il2_sort32_asc(x, lane), lane);
+    const int n = cnt < 32 ? cnt : 32;
+    uint64_t x = DFX_COMP_NONE;
+    if (lane < n) {
+        const uint64_t c = queue[lane];
+        x = (c & 0xffffffff00000000ull) | (uint64_t)dfx_ld_nc_u(il_ids + (uint32_t)c);
     }
-    __syncwarp();  // queue fully read before later pushes overwrite it
+    const int rest = cnt - n;  // < 32: the pusher flushes as soon as 32 entries are queued
+    const uint64_t moved = (lane < rest) ? queue[32 + lane] : 0;
+    __syncwarp();  // queue fully read before it is rewritten
+    if (lane < rest) queue[lane] = moved;
+    __syncwarp();
+    kept = il2_merge_sorted(kept, il2_sort32_asc(x, lane), lane);
     const uint64_t kth = __shfl_sync(0xffffffffu, kept, k - 1);
     if (kth != DFX_COMP_NONE) {
         thr = dfx_key2f((uint32_t)(kth >> 32));
@@ -106,6 +111,7 @@ __device__ __noinline__ Il2Flushed il2_flush(uint64_t kept, const uint64_t* queu
     r.kept = kept;
     r.thr = thr;
     r.thr_sec = thr_sec;
+    r.cnt = rest;
     return r;
 }
 
@@ -158,13 +164,13 @@ scan_pq_il2_kernel(const float* __restrict__ lutW, const float* __restrict__ dis
     float bnd = __int_as_float(0x7f800000);  // register copy of the CTA bound (may lag: only looser)
     if (!REG) wt.init(s_buf + (size_t)warp * cap, cap, k, &s_cta_key);
 
-    // merge the queue into `kept` (out of line: rare, and called from three places)
+    // merge 32 queued candidates into `kept` (out of line: rare, and called from three places)
     auto flush = [&]() {
         const Il2Flushed f = il2_flush(kept, queue, cnt, k, il_ids, &s_cta_key, thr, thr_sec, lane);
         kept = f.kept;
         thr = f.thr;
         thr_sec = f.thr_sec;
-        cnt = 0;
+        cnt = f.cnt;
     };
 
     dfx_bulk_wait(&s_lut_bar);
@@ -214,7 +220,7 @@ scan_pq_il2_kernel(const float* __restrict__ lutW, const float* __restrict__ dis
                             ((uint64_t)dfx_f2key(v) << 32) | (uint64_t)((uint32_t)pos * 32u + (uint32_t)lane);
                     cnt += __popc(mask);
                     __syncwarp();
-                    if (cnt > IL2_QCAP - 32) flush();
+                    if (cnt >= 32) flush();  // keeps cnt <= 31 between pushes (a push adds <= 32)
                 }
             }
         } else {

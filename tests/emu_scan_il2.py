@@ -119,17 +119,19 @@ class Warp:
         self.flushes = 0
 
     def flush(self):
+        """il2_flush: merge the first min(cnt, 32) entries, move the rest to the front"""
         cta = self.cta
-        for base in range(0, self.cnt, 32):
-            e = base + LANES
-            x = np.full(32, NONE, dtype=np.uint64)
-            live = e < self.cnt
-            c = self.queue[np.minimum(e, QCAP - 1)]
-            ids = cta.il_ids.reshape(-1)[(c & np.uint64(0xFFFFFFFF)).astype(np.int64)].astype(np.int64)
-            comp = (c & np.uint64(0xFFFFFFFF00000000)) | (ids & 0xFFFFFFFF).astype(np.uint64)
-            x = np.where(live, comp, x)
-            self.kept = merge_sorted(self.kept, sort32_asc(x))
-        self.cnt = 0
+        n = min(self.cnt, 32)
+        x = np.full(32, NONE, dtype=np.uint64)
+        live = LANES < n
+        c = self.queue[LANES]
+        ids = cta.il_ids.reshape(-1)[(c & np.uint64(0xFFFFFFFF)).astype(np.int64) % cta.il_ids.size].astype(np.int64)
+        comp = (c & np.uint64(0xFFFFFFFF00000000)) | (ids & 0xFFFFFFFF).astype(np.uint64)
+        x = np.where(live, comp, x)
+        rest = self.cnt - n
+        self.queue[:rest] = self.queue[32:32 + rest].copy()
+        self.kept = merge_sorted(self.kept, sort32_asc(x))
+        self.cnt = rest
         self.flushes += 1
         kth = self.kept[self.k - 1]
         if kth != NONE:
@@ -155,7 +157,7 @@ class Warp:
         comp = (f2key(v).astype(np.uint64) << np.uint64(32)) | (np.uint64(pos) * np.uint64(32) + LANES.astype(np.uint64))
         self.queue[slot[want]] = comp[want]
         self.cnt += int(want.sum())
-        if self.cnt > QCAP - 32:
+        if self.cnt >= 32:
             self.flush()
 
     def stream(self):
