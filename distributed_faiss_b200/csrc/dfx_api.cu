@@ -79,7 +79,7 @@ int dfx_create(const dfx_cfg* cfg, dfx_index** out) {
         idx->dsub = cfg->d / cfg->pq_m;
         // experiments: DFX_SCAN_VARIANT=2 makes new indexes start on the lane-per-vector scan
         if (const char* e = getenv("DFX_SCAN_VARIANT"))
-            if (atoi(e) == 2) idx->il_variant = 2;
+            if (atoi(e) == 2 || atoi(e) == 3) idx->il_variant = atoi(e);
         if (const char* e = getenv("DFX_PREP_VARIANT"))
             if (atoi(e) == 2) idx->prep_variant = 2;
     }
@@ -126,8 +126,9 @@ int dfx_set_param(dfx_index* idx, const char* name, double value) {
     }
     else if (n == "scan_variant") {
         // 1 = scan_pq_il_kernel (8 lanes per vector), 2 = scan_pq_il2_kernel (lane per vector,
-        // wide table); changes the block layout, so resident blocks are converted
-        DFX_REQUIRE(value == 1 || value == 2, "scan_variant must be 1 or 2");
+        // wide table), 3 = scan_pq_il_split_kernel (1 on coalesced halves); changes the block
+        // layout, so resident blocks are converted
+        DFX_REQUIRE(value == 1 || value == 2 || value == 3, "scan_variant must be 1, 2 or 3");
         std::lock_guard<std::mutex> lk(idx->mu);
         DeviceGuard g(idx->cfg.device);
         idx->join_dev();

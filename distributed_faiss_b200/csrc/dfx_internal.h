@@ -41,7 +41,8 @@ struct dfx_index {
     DevBuf il_codes, il_tvals, il_ids, blk_off;
     int64_t nblk = 0;
     // which block layout / scan kernel: 1 = dfx_il_byte + scan_pq_il_kernel (default),
-    // 2 = dfx_il2_byte + scan_pq_il2_kernel (dfx_scan_il2.cu; dfx_set_param "scan_variant")
+    // 2 = dfx_il2_byte + scan_pq_il2_kernel (dfx_scan_il2.cu; dfx_set_param "scan_variant"),
+    // 3 = dfx_il3_byte + scan_pq_il_split_kernel (the default kernel on coalesced halves)
     // K3 variant (dfx_set_param "prep_variant"): 2 = pq_prep2_kernel on the transposed codebook
     int prep_variant = 1;
     DevBuf codebooksT;  // [ksub][M][dsub], built on demand
@@ -140,8 +141,13 @@ __host__ __device__ __forceinline__ int dfx_il2_byte(int v, int m) {
     const int t = (m - v) & 31;
     return (t >> 4) * 512 + v * 16 + (t & 15);
 }
+// Layout 3: the words of layout 1 with each lane's two 16-byte halves stored 512 bytes apart.
+__host__ __device__ __forceinline__ int dfx_il3_byte(int v, int m) {
+    const int b = dfx_il_byte(v, m), lane = b >> 5, r = (b >> 2) & 7, t = b & 3;
+    return (r >> 2) * 512 + lane * 16 + (r & 3) * 4 + t;
+}
 __host__ __device__ __forceinline__ int dfx_il_byte_of(int layout, int v, int m) {
-    return layout == 2 ? dfx_il2_byte(v, m) : dfx_il_byte(v, m);
+    return layout == 2 ? dfx_il2_byte(v, m) : layout == 3 ? dfx_il3_byte(v, m) : dfx_il_byte(v, m);
 }
 
 // ---- dfx_scan_il.cu
@@ -149,7 +155,7 @@ bool dfx_il_wanted(const dfx_index* idx);
 void dfx_pq_rm_to_il(dfx_index* idx, cudaStream_t st);
 void dfx_pq_il_to_rm(dfx_index* idx, cudaStream_t st);
 void dfx_launch_scan_pq_il(dfx_index* idx, int64_t qc, const int32_t* keys, int nprobe, int G, int ngroups,
-                           int k, int cap, uint64_t* part, cudaStream_t st);
+                           int k, int cap, uint64_t* part, cudaStream_t st);  // layout 1 or 3
 // ---- dfx_scan_il2.cu  (lutW: [nq][256][64] wide table, see pq_prep_kernel mode 2)
 void dfx_launch_scan_pq_il2(dfx_index* idx, int64_t qc, const int32_t* keys, int nprobe, int G, int ngroups,
                             int k, int cap, uint64_t* part, cudaStream_t st);

@@ -65,7 +65,7 @@ void dfx_pq_il_to_rm(dfx_index* idx, cudaStream_t st) {
 void dfx_launch_scan_pq_il(dfx_index* idx, int64_t qc, const int32_t* keys, int nprobe, int G, int ngroups, int k,
                            int cap, uint64_t* part, cudaStream_t st) {
     const size_t smem = (size_t)256 * 32 * 4 + (size_t)(IL_THREADS / 32) * cap * 8;
-    auto kern = scan_pq_il_kernel;
+    auto kern = (idx->il_layout == 3) ? scan_pq_il_split_kernel : scan_pq_il_kernel;
     DFX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     DFX_LAUNCH(kern, (unsigned)(qc * ngroups), IL_THREADS, smem, st, idx->w_lut.as<float>(), idx->w_dis0.as<float>(), keys,
                nprobe, G, ngroups, idx->blk_off.as<int64_t>(), idx->il_codes.as<uint4>(), idx->il_tvals.as<float>(),

@@ -80,11 +80,16 @@ pq_il_to_rm_kernel(const int64_t* __restrict__ list_off, const int64_t* __restri
 // ------------------------------------------------------------------ the scan
 // lutT: [nq][256][32] (transposed table, written by pq_prep_kernel)
 constexpr int IL_THREADS = 256;  // 8 warps: 4 CTAs/SM = 32 warps/SM (the 64-register limit)
-__global__ void __launch_bounds__(IL_THREADS, 4)
-scan_pq_il_kernel(const float* __restrict__ lutT, const float* __restrict__ dis0, const int32_t* __restrict__ keys,
-                  int nprobe, int G, int ngroups, const int64_t* __restrict__ blk_off,
-                  const uint4* __restrict__ il_codes, const float* __restrict__ il_tvals,
-                  const int32_t* __restrict__ il_ids, int k, int cap, uint64_t* __restrict__ part) {
+// SPLIT: block layout 3 -- the same words as layout 1, but the two 16-byte halves of a lane's 32
+// bytes are stored 512 bytes apart ([half][lane][16]) so that each 128-bit load of the warp is one
+// contiguous 512-byte run (layout 1: lanes 32 bytes apart, every load touches all 8 lines of the
+// block and each sector crosses the L2->L1 crossbar twice).
+template <bool SPLIT>
+__device__ __forceinline__ void
+scan_pq_il_body(const float* __restrict__ lutT, const float* __restrict__ dis0, const int32_t* __restrict__ keys,
+                int nprobe, int G, int ngroups, const int64_t* __restrict__ blk_off,
+                const uint4* __restrict__ il_codes, const float* __restrict__ il_tvals,
+                const int32_t* __restrict__ il_ids, int k, int cap, uint64_t* __restrict__ part) {
     DFX_DYN_SMEM(unsigned char, smem_raw, 16);
     float* s_lut = reinterpret_cast<float*>(smem_raw);                       // [256][32]
     uint64_t* s_buf = reinterpret_cast<uint64_t*>(smem_raw + 256 * 32 * 4);  // 8 warps x cap
@@ -153,10 +158,11 @@ scan_pq_il_kernel(const float* __restrict__ lutT, const float* __restrict__ dis0
         // this lane's slice of block i of the warp: codes 2 x 16 B, t 4 B, id 4 B, streamed one
         // block ahead (an id fetched only on admission would put a DRAM latency on the critical
         // path of every admission)
-        const uint4* pc = il_codes + b0 * 64 + lane * 2;
+        const uint4* pc = il_codes + b0 * 64 + (SPLIT ? lane : lane * 2);
+        constexpr int HALF = SPLIT ? 32 : 1;  // distance (in uint4) between a lane's two halves
         const float* pt = il_tvals + b0 * 32 + lane;
         const int32_t* pi = il_ids + b0 * 32 + lane;
-        uint4 xa = dfx_ld_stream(pc), xb = dfx_ld_stream(pc + 1);
+        uint4 xa = dfx_ld_stream(pc), xb = dfx_ld_stream(pc + HALF);
         float xt = dfx_ld_stream_f(pt);
         uint32_t xi = dfx_ld_stream_u(pi);
         for (int64_t i = 0; i < nb; i++) {
@@ -168,7 +174,7 @@ scan_pq_il_kernel(const float* __restrict__ lutT, const float* __restrict__ dis0
                 pt += S * 32;
                 pi += S * 32;
                 xa = dfx_ld_stream(pc);
-                xb = dfx_ld_stream(pc + 1);
+                xb = dfx_ld_stream(pc + HALF);
                 xt = dfx_ld_stream_f(pt);
                 xi = dfx_ld_stream_u(pi);
             }
@@ -176,5 +182,22 @@ scan_pq_il_kernel(const float* __restrict__ lutT, const float* __restrict__ dis0
         }
     }
     cta_merge_and_write<IL_THREADS>(wt, s_buf, cap, k, part + ((int64_t)q * ngroups + g) * k);
+}
+
+__global__ void __launch_bounds__(IL_THREADS, 4)
+scan_pq_il_kernel(const float* __restrict__ lutT, const float* __restrict__ dis0, const int32_t* __restrict__ keys,
+                  int nprobe, int G, int ngroups, const int64_t* __restrict__ blk_off,
+                  const uint4* __restrict__ il_codes, const float* __restrict__ il_tvals,
+                  const int32_t* __restrict__ il_ids, int k, int cap, uint64_t* __restrict__ part) {
+    scan_pq_il_body<false>(lutT, dis0, keys, nprobe, G, ngroups, blk_off, il_codes, il_tvals, il_ids, k, cap, part);
+}
+// EXPERIMENTAL (scan_variant = 3): the same kernel on block layout 3
+__global__ void __launch_bounds__(IL_THREADS, 4)
+scan_pq_il_split_kernel(const float* __restrict__ lutT, const float* __restrict__ dis0,
+                        const int32_t* __restrict__ keys, int nprobe, int G, int ngroups,
+                        const int64_t* __restrict__ blk_off, const uint4* __restrict__ il_codes,
+                        const float* __restrict__ il_tvals, const int32_t* __restrict__ il_ids, int k, int cap,
+                        uint64_t* __restrict__ part) {
+    scan_pq_il_body<true>(lutT, dis0, keys, nprobe, G, ngroups, blk_off, il_codes, il_tvals, il_ids, k, cap, part);
 }
 

@@ -604,7 +604,7 @@ void dfx_search_impl(dfx_index* idx, int64_t nq, const float* d_x, int64_t k64, 
             } else
             DFX_LAUNCH(pq_prep_kernel, (unsigned)qc, 256, prep_smem, st, xq, d, M, ksub, idx->dsub,
                        idx->codebooks.as<float>(), idx->centroids.as<float>(), keys, nprobe,
-                       idx->w_lut.as<float>(), idx->w_dis0.as<float>(), il);
+                       idx->w_lut.as<float>(), idx->w_dis0.as<float>(), il == 3 ? 1 : il);
             if (il == 2) {
                 dfx_launch_scan_pq_il2(idx, qc, keys, nprobe, G, ngroups, k, cap, part, st);
             } else if (il) {

@@ -61,12 +61,17 @@ int emu_pq_prep2(const float* Q, int64_t nq, int d, const float* codebooks, cons
 
 int emu_scan_v2(const float* lutT, const float* dis0, const int32_t* keys, int64_t nq, int nprobe, int G, int ngroups,
                 const int64_t* blk_off, const uint8_t* il_codes, const float* il_tvals, const int32_t* il_ids, int k,
-                int cap, uint64_t* part) {
+                int cap, uint64_t* part, int split) {
     const size_t smem = (size_t)256 * 32 * 4 + (size_t)(IL_THREADS / 32) * cap * 8;
-    simt::launch((unsigned)(nq * ngroups), IL_THREADS, smem, [=] {
-        scan_pq_il_kernel(lutT, dis0, keys, nprobe, G, ngroups, blk_off, reinterpret_cast<const uint4*>(il_codes),
-                          il_tvals, il_ids, k, cap, part);
-    }, g_seed);
+    const uint4* c4 = reinterpret_cast<const uint4*>(il_codes);
+    if (split)  // block layout 3
+        simt::launch((unsigned)(nq * ngroups), IL_THREADS, smem, [=] {
+            scan_pq_il_split_kernel(lutT, dis0, keys, nprobe, G, ngroups, blk_off, c4, il_tvals, il_ids, k, cap, part);
+        }, g_seed);
+    else
+        simt::launch((unsigned)(nq * ngroups), IL_THREADS, smem, [=] {
+            scan_pq_il_kernel(lutT, dis0, keys, nprobe, G, ngroups, blk_off, c4, il_tvals, il_ids, k, cap, part);
+        }, g_seed);
     return 0;
 }
 

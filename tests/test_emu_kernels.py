@@ -93,14 +93,14 @@ class Pipeline:
         keys64, _ = O.coarse(st["coarse_metric"], st["centroids"], xq, nprobe)
         keys = np.ascontiguousarray(keys64, dtype=np.int32)
         nq = xq.shape[0]
-        width = 64 if self.layout == 2 else 32
+        width = 64 if self.layout == 2 else 32            # layouts 1 and 3 share the [code][m] table
         lut = np.full((nq, 256, width), np.nan, dtype=np.float32)
         dis0 = np.full((nq, nprobe), np.nan, dtype=np.float32)
         cb = np.ascontiguousarray(st["codebooks"], dtype=np.float32)
         cent = np.ascontiguousarray(st["centroids"], dtype=np.float32)
         xq = np.ascontiguousarray(xq, dtype=np.float32)
         self.lib.emu_pq_prep(_p(xq), C.c_int64(nq), d, M, 256, d // M, _p(cb), _p(cent), _p(keys), nprobe,
-                             _p(lut), _p(dis0), self.layout)
+                             _p(lut), _p(dis0), 2 if self.layout == 2 else 1)
         return keys, lut, dis0
 
     def search(self, xq, k, nprobe, G):
@@ -112,9 +112,12 @@ class Pipeline:
             KP *= 2
         cap = 2 * KP
         part = np.full((nq, ngroups, k), 0x1234, dtype=np.uint64)
-        fn = self.lib.emu_scan_v3 if self.layout == 2 else self.lib.emu_scan_v2
-        rc = fn(_p(lut), _p(dis0), _p(keys), C.c_int64(nq), nprobe, G, ngroups, _p(self.blk_off), _p(self.il_codes),
+        args = (_p(lut), _p(dis0), _p(keys), C.c_int64(nq), nprobe, G, ngroups, _p(self.blk_off), _p(self.il_codes),
                 _p(self.il_tvals), _p(self.il_ids), k, cap, _p(part))
+        if self.layout == 2:
+            rc = self.lib.emu_scan_v3(*args)
+        else:  # layout 1: shipping kernel; layout 3: the same kernel on coalesced halves
+            rc = self.lib.emu_scan_v2(*args, 1 if self.layout == 3 else 0)
         assert rc == 0
         D = np.full((nq, k), np.inf, dtype=np.float32)
         I = np.full((nq, k), -1, dtype=np.int64)
@@ -143,7 +146,7 @@ def built():
     return _index()
 
 
-@pytest.mark.parametrize("layout", [1, 2])
+@pytest.mark.parametrize("layout", [1, 2, 3])
 def test_layout_conversion_round_trip(emu, built, layout):
     ix, _, _ = built
     p = Pipeline(emu, ix, layout)
@@ -164,7 +167,10 @@ def emu_byte(layout, v, m):
     if layout == 2:
         return (t >> 4) * 512 + v * 16 + (t & 15)
     u, w, i, j = v >> 3, v & 7, m & 7, m >> 3
-    return (8 * u + i) * 32 + (w ^ i) * 4 + ((j - u) & 3)
+    lane, r, tt = 8 * u + i, w ^ i, (j - u) & 3
+    if layout == 3:
+        return (r >> 2) * 512 + lane * 16 + (r & 3) * 4 + tt
+    return lane * 32 + r * 4 + tt
 
 
 @pytest.mark.parametrize("layout", [1, 2])
@@ -204,6 +210,7 @@ CASES = [  # layout, k, nprobe, G, scheduler seed
     (1, 10, 4, 4, 0), (1, 10, 4, 1, 7),                   # shipping kernel: validates the emulator itself
     (2, 10, 4, 4, 0), (2, 10, 4, 1, 7), (2, 1, 3, 2, 3), (2, 32, 8, 8, 11),   # v3, register top-k
     (2, 40, 4, 4, 0), (2, 100, 8, 3, 5),                  # v3, shared-memory top-k (k > 32)
+    (3, 10, 4, 4, 0), (3, 50, 5, 2, 9),                   # shipping kernel on block layout 3
 ]
 
 
@@ -220,7 +227,7 @@ def test_scan_kernels_equal_oracle(emu, built, layout, k, nprobe, G, seed):
     assert D.tobytes() == Dref.tobytes()
 
 
-@pytest.mark.parametrize("layout", [1, 2])
+@pytest.mark.parametrize("layout", [1, 2, 3])
 def test_scan_kernels_short_lists(emu, layout):
     """lists shorter than a block, empty lists, fewer than k results"""
     ix, x, rs = _index(n=2000, nlist=8, dup=0, seed=4, n_add=21)

@@ -436,10 +436,14 @@ def test_scan_variant_2_matches_oracle():
         g.set_param("scan_variant", 2)
         _assert_same(*g.search(xq, k), Do, Io, f"variant 2 nprobe={nprobe} k={k}")
         R2 = g.reconstruct_rows(ids)
+        g.set_param("scan_variant", 3)                # the shipping kernel on coalesced halves
+        _assert_same(*g.search(xq, k), Do, Io, f"variant 3 nprobe={nprobe} k={k}")
+        R3 = g.reconstruct_rows(ids)
         g.set_param("scan_variant", 1)
         _assert_same(*g.search(xq, k), Do, Io, f"variant 1 nprobe={nprobe} k={k}")
         R1 = g.reconstruct_rows(ids)
         assert np.array_equal(R1[[0, 1, 2, 4]], R2[[0, 1, 2, 4]]) and np.isnan(R2[3]).all()
+        assert np.array_equal(R1[[0, 1, 2, 4]], R3[[0, 1, 2, 4]])
     g.set_param("scan_variant", 2)
     for nq in (1, 3, 200):                           # one list per CTA at small batches
         q = np.ascontiguousarray(np.tile(xq, (6, 1))[:nq])

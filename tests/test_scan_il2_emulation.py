@@ -21,7 +21,7 @@ def lib():
     return ctypes.CDLL(engine.LIB_PATH)
 
 
-@pytest.mark.parametrize("layout", [1, 2])
+@pytest.mark.parametrize("layout", [1, 2, 3])
 def test_block_layout_is_a_bijection(lib, layout):
     t = emu.il_byte_table(lib, layout)
     assert sorted(t.reshape(-1).tolist()) == list(range(1024))
