@@ -1,5 +1,5 @@
 // simt.h -- a tiny SIMT runtime for the CPU emulator: one CTA at a time, every CUDA thread is a
-// ucontext fiber on ONE OS thread; fibers run until they reach a collective (warp exchange,
+// fiber on ONE OS thread; fibers run until they reach a collective (warp exchange,
 // ballot, __syncwarp, __syncthreads) or an explicit yield, where the next fiber is scheduled.
 // Collectives are full-warp (all 32 lanes must arrive), which is how the scan kernels use them.
 // Dynamic shared memory is filled with a poison pattern before each CTA; shared-memory reads by
@@ -9,15 +9,59 @@
 #include <string.h>
 #include <stdio.h>
 #include <stdlib.h>
-#include <ucontext.h>
 #include <functional>
 #include <vector>
+
+// Context switch.  glibc's swapcontext saves/restores the signal mask with a system call on every
+// switch, which dominates the run time of an emulated kernel (millions of switches); on x86-64 a
+// dozen instructions that swap the callee-saved registers and the stack pointer do the same job.
+#if defined(__x86_64__)
+extern "C" void simt_switch(void** save_sp, void* load_sp);
+asm(R"(
+.text
+.globl simt_switch
+.type simt_switch,@function
+simt_switch:
+    pushq %rbp
+    pushq %rbx
+    pushq %r12
+    pushq %r13
+    pushq %r14
+    pushq %r15
+    movq %rsp, (%rdi)
+    movq %rsi, %rsp
+    popq %r15
+    popq %r14
+    popq %r13
+    popq %r12
+    popq %rbx
+    popq %rbp
+    ret
+.size simt_switch,.-simt_switch
+)");
+#else
+#error "tests/emu/simt.h: only x86-64 is supported (tests/test_emu_kernels.py skips elsewhere)"
+#endif
+
+#if defined(__SANITIZE_ADDRESS__)
+#include <sanitizer/common_interface_defs.h>
+#define SIMT_ASAN_START(save, bottom, size) __sanitizer_start_switch_fiber(save, bottom, size)
+#define SIMT_ASAN_FINISH(save, bottom, size) __sanitizer_finish_switch_fiber(save, bottom, size)
+#include <sanitizer/asan_interface.h>
+#define SIMT_ASAN_POISON(p, n) __asan_poison_memory_region(p, n)
+#define SIMT_ASAN_UNPOISON(p, n) __asan_unpoison_memory_region(p, n)
+#else
+#define SIMT_ASAN_POISON(p, n) ((void)0)
+#define SIMT_ASAN_UNPOISON(p, n) ((void)0)
+#define SIMT_ASAN_START(save, bottom, size) ((void)0)
+#define SIMT_ASAN_FINISH(save, bottom, size) ((void)0)
+#endif
 
 namespace simt {
 
 struct Tid { unsigned x, y, z; };
 struct Fiber {
-    ucontext_t ctx;
+    void* sp;  // saved stack pointer while the fiber is not running
     Tid tid;
     bool done;
 };
@@ -31,7 +75,7 @@ struct State {
     std::vector<Warp> warps;
     int nthreads = 0, cur = -1;
     int bar_arrive = 0, bar_gen = 0;
-    ucontext_t sched;
+    void* sched_sp = nullptr;
     std::vector<unsigned char> dyn;
     std::function<void()> kernel;
     uint64_t rng = 0;  // != 0: fibers are resumed in a pseudo-random order
@@ -60,9 +104,15 @@ inline unsigned char* smem_ptr(uint32_t addr) {
     }
     return S().dyn.data() + addr;
 }
+inline const void* g_sched_bottom = nullptr;  // the scheduler's stack, as AddressSanitizer sees it
+inline size_t g_sched_size = 0;
 inline void yield() {
     S().switches++;
-    swapcontext(&S().fibers[S().cur].ctx, &S().sched);
+    void* fake = nullptr;
+    (void)fake;
+    SIMT_ASAN_START(&fake, g_sched_bottom, g_sched_size);
+    simt_switch(&S().fibers[S().cur].sp, S().sched_sp);
+    SIMT_ASAN_FINISH(fake, &g_sched_bottom, &g_sched_size);
 }
 inline void warp_barrier() {
     Warp& w = S().warps[S().cur >> 5];
@@ -113,9 +163,12 @@ inline unsigned warp_ballot(bool pred) {
 
 inline void fiber_entry() {
     State& s = S();
+    SIMT_ASAN_FINISH(nullptr, &g_sched_bottom, &g_sched_size);
     s.kernel();
     s.fibers[s.cur].done = true;
-    swapcontext(&s.fibers[s.cur].ctx, &s.sched);
+    SIMT_ASAN_START(nullptr, g_sched_bottom, g_sched_size);  // this fiber never resumes
+    simt_switch(&s.fibers[s.cur].sp, s.sched_sp);
+    abort();
 }
 
 // run `kernel` (a closure over the kernel arguments) on grid x block threads, dyn_bytes of
@@ -135,8 +188,13 @@ inline void launch(unsigned grid, unsigned block, size_t dyn_bytes, std::functio
     s.stacks.resize((size_t)block * STACK);
     for (unsigned b = 0; b < grid; b++) {
         g_block = {b, 0, 0};
-        s.dyn.assign(dyn_bytes + 16, 0xCD);  // poison: reads of unwritten shared memory show up as garbage
+        // filled with a pattern (reads of unwritten shared memory show up as garbage); the slack
+        // behind the requested size is poisoned for AddressSanitizer, so that any access past the
+        // end of the dynamic shared memory aborts (the buffer itself is reused: no reallocation)
+        SIMT_ASAN_UNPOISON(s.dyn.data(), s.dyn.capacity());
+        s.dyn.assign(dyn_bytes + 256, 0xCD);
         s.dyn.resize(dyn_bytes);
+        SIMT_ASAN_POISON(s.dyn.data() + dyn_bytes, s.dyn.capacity() - dyn_bytes);
         s.fibers.assign(block, Fiber());
         s.warps.assign(block / 32, Warp());
         for (auto& w : s.warps) w.arrive = w.gen = 0;
@@ -146,11 +204,14 @@ inline void launch(unsigned grid, unsigned block, size_t dyn_bytes, std::functio
             Fiber& f = s.fibers[t];
             f.tid = {t, 0, 0};
             f.done = false;
-            getcontext(&f.ctx);
-            f.ctx.uc_stack.ss_sp = s.stacks.data() + (size_t)t * STACK;
-            f.ctx.uc_stack.ss_size = STACK;
-            f.ctx.uc_link = nullptr;
-            makecontext(&f.ctx, fiber_entry, 0);
+            // initial frame: six callee-saved registers, then fiber_entry as the return target;
+            // at entry the stack pointer is 8 below a 16-byte boundary, as after a call
+            uintptr_t top = reinterpret_cast<uintptr_t>(s.stacks.data() + (size_t)(t + 1) * STACK) & ~(uintptr_t)15;
+            void** frame = reinterpret_cast<void**>(top - 64);
+            for (int r = 0; r < 6; r++) frame[r] = nullptr;
+            frame[6] = reinterpret_cast<void*>(&fiber_entry);
+            frame[7] = nullptr;
+            f.sp = frame;
         }
         int live = (int)block;
         long stale_sweeps = 0;
@@ -164,7 +225,13 @@ inline void launch(unsigned grid, unsigned block, size_t dyn_bytes, std::functio
                 }
                 if (s.fibers[t].done) continue;
                 s.cur = (int)t;
-                swapcontext(&s.sched, &s.fibers[t].ctx);
+                {
+                    void* fake = nullptr;
+                    (void)fake;
+                    SIMT_ASAN_START(&fake, s.stacks.data() + (size_t)t * STACK, STACK);
+                    simt_switch(&s.sched_sp, s.fibers[t].sp);
+                    SIMT_ASAN_FINISH(fake, nullptr, nullptr);
+                }
                 if (s.fibers[t].done) {
                     live--;
                     s.events++;
@@ -177,6 +244,7 @@ inline void launch(unsigned grid, unsigned block, size_t dyn_bytes, std::functio
             }
         }
         s.cur = -1;
+        SIMT_ASAN_UNPOISON(s.dyn.data(), s.dyn.capacity());
     }
 }
 

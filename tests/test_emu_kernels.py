@@ -237,3 +237,24 @@ def test_scan_kernels_short_lists(emu, layout):
     D, I, _ = Pipeline(emu, ix, layout, 3).search(xq, 32, 8, 8)
     assert np.array_equal(I, Iref) and (I[:, 21:] == -1).all()
     assert D[:, :21].tobytes() == Dref[:, :21].tobytes()
+
+
+def test_emulated_kernels_under_address_sanitizer(tmp_path):
+    """CPU stand-in for compute-sanitizer memcheck: every emulated kernel on random ragged shards
+    with exact-size allocations, under ASan + UBSan (tests/emu/emu_memcheck.cpp)"""
+    cxx = shutil.which("g++")
+    if cxx is None:
+        pytest.skip("g++ not available")
+    exe = str(tmp_path / "emu_memcheck")
+    csrc = os.path.join(ROOT, "distributed_faiss_b200", "csrc")
+    cmd = [cxx, "-std=c++17", "-O1", "-g", "-fsanitize=address,undefined", "-fno-sanitize-recover=undefined",
+           "-fno-omit-frame-pointer", "-ffp-contract=off", "-DDFX_EMU", "-Wno-unknown-pragmas", "-Wno-attributes",
+           "-I", os.path.join(EMU_DIR, "shim"), "-I", csrc, "-I", EMU_DIR, "-o", exe,
+           os.path.join(EMU_DIR, "emu_memcheck.cpp")]
+    probe = subprocess.run(cmd, capture_output=True, text=True)
+    if probe.returncode != 0 and "sanitize" in probe.stderr and "cannot find" in probe.stderr:
+        pytest.skip("sanitizer runtime not installed")
+    assert probe.returncode == 0, probe.stderr[-2000:]
+    env = dict(os.environ, ASAN_OPTIONS="detect_stack_use_after_return=0")
+    run = subprocess.run([exe], capture_output=True, text=True, env=env, timeout=900)
+    assert run.returncode == 0 and "memcheck ok" in run.stdout, (run.stdout + run.stderr)[-3000:]
