@@ -9,6 +9,7 @@
 // trained on residuals of <= 256*ksub training vectors; add = nearest centroid under the
 // quantizer's metric, ids sequential, ids ascending inside every list.
 #include "dfx_internal.h"
+#include "dfx_ptx.cuh"
 #include <cub/cub.cuh>
 #include <algorithm>
 #include <numeric>
@@ -82,7 +83,7 @@ __global__ void __launch_bounds__(256)
 pq_encode_kernel(const float* __restrict__ x, const float* __restrict__ cent,
                  const int32_t* __restrict__ assign, int64_t n, int d, int M, int ksub, int dsub,
                  const float* __restrict__ codebooks, uint8_t* __restrict__ codes) {
-    extern __shared__ float s_cb[];  // [ksub][dsub]
+    DFX_DYN_SMEM0(float, s_cb);  // [ksub][dsub]
     const int m = blockIdx.y;
     for (int i = threadIdx.x; i < ksub * dsub; i += blockDim.x)
         s_cb[i] = codebooks[(size_t)m * ksub * dsub + i];

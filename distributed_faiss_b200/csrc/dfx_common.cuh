@@ -32,6 +32,16 @@ struct DfxError {
     } while (0)
 
 // every kernel launch goes through this so that dfx_launch_count() is honest
+#ifdef DFX_EMU
+// CPU emulator build (tests/emu/, never a product build): the kernel runs on the fiber SIMT
+// runtime, one CTA after the other, synchronously
+#define DFX_LAUNCH(kernel, grid, block, smem, stream, ...)                                      \
+    do {                                                                                        \
+        const dim3 _g(grid), _b(block);                                                         \
+        simt::launch3(_g.x, _g.y, _b.x, (size_t)(smem), [&]() { kernel(__VA_ARGS__); });         \
+        g_dfx_launches.fetch_add(1, std::memory_order_relaxed);                                 \
+    } while (0)
+#else
 #define DFX_LAUNCH(kernel, grid, block, smem, stream, ...)                                      \
     do {                                                                                        \
         const dim3 _g(grid), _b(block);                                                         \
@@ -44,6 +54,7 @@ struct DfxError {
                            std::to_string(_b.x) + " smem=" + std::to_string((size_t)(smem)) + " (" +  \
                            __FILE__ + ":" + std::to_string(__LINE__) + ")"};                    \
     } while (0)
+#endif
 
 // grow-only device buffer
 struct DevBuf {

@@ -13,6 +13,7 @@
 #include "dfx_internal.h"
 #include "dfx_select.cuh"
 #include "dfx_topk.cuh"
+#include "dfx_ptx.cuh"
 
 // =====================================================================================
 // K1a: values GEMM (fp32 FFMA).  acc = fmaf(q[k], x[k], acc), k ascending.
@@ -198,7 +199,7 @@ scan_pq_kernel(const float* __restrict__ lut, const float* __restrict__ dis0,
                const int64_t* __restrict__ list_off, const uint8_t* __restrict__ codes,
                const float* __restrict__ tvals, const int32_t* __restrict__ ids, int Mrt, int ksub,
                int k, int cap, uint64_t* __restrict__ part) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    DFX_DYN_SMEM(unsigned char, smem_raw, 16);
     const int M = (MT > 0) ? MT : Mrt;
     float* s_lut = reinterpret_cast<float*>(smem_raw);
     uint64_t* s_buf = reinterpret_cast<uint64_t*>(smem_raw + (size_t)M * ksub * 4);
@@ -288,7 +289,7 @@ scan_rows_kernel(const float* __restrict__ Q, int d, const float* __restrict__ c
                  const int32_t* __restrict__ keys, int nprobe, int G, int ngroups,
                  const int64_t* __restrict__ list_off, const void* __restrict__ rows,
                  const int32_t* __restrict__ ids, int k, int cap, uint64_t* __restrict__ part) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    DFX_DYN_SMEM(unsigned char, smem_raw, 16);
     float* s_q = reinterpret_cast<float*>(smem_raw);   // query (MODE 2: residual q - c)
     float* s_q0 = s_q + d;                              // MODE 2: the raw query
     const int dpad = (MODE == 2) ? 2 * d : d;

@@ -11,6 +11,7 @@
 // most `sort_cap` elements skip the radix passes and are sorted directly.
 #pragma once
 #include "dfx_common.cuh"
+#include "dfx_ptx.cuh"
 
 template <int THREADS>
 __device__ __forceinline__ void dfx_block_bitonic_sort(uint64_t* s, int P) {
@@ -32,14 +33,13 @@ __device__ __forceinline__ void dfx_block_bitonic_sort(uint64_t* s, int P) {
     __syncthreads();
 }
 
-#ifndef DFX_EMU  // the row-selection kernel and its launcher are not part of the CPU emulator build
 // Loader:  __device__ uint64_t operator()(int64_t row, int e) const   (DFX_COMP_NONE = no candidate)
 // Writer:  __device__ void operator()(int64_t row, int j, uint64_t comp) const   (j in [0,k))
 // dynamic smem: P * 8 bytes with P = pow2 >= max(k, min(n, sort_cap))
 template <int THREADS, class Loader, class Writer>
 __global__ void __launch_bounds__(THREADS) dfx_select_rows_kernel(Loader ld, Writer wr, int n, int k,
                                                                  int P, int sort_cap) {
-    extern __shared__ __align__(16) unsigned char dfx_sel_smem[];
+    DFX_DYN_SMEM(unsigned char, dfx_sel_smem, 16);
     uint64_t* s_out = reinterpret_cast<uint64_t*>(dfx_sel_smem);
     __shared__ int s_hist[256];
     __shared__ int s_cnt;
@@ -149,4 +149,3 @@ static inline void dfx_launch_select(Loader ld, Writer wr, int64_t nrows, int n,
     auto kern = dfx_select_rows_kernel<THREADS, Loader, Writer>;
     DFX_LAUNCH(kern, (unsigned)nrows, THREADS, smem, st, ld, wr, n, k, P, sort_cap);
 }
-#endif

@@ -3,6 +3,7 @@
 // same headers nvcc compiles (distributed_faiss_b200/csrc/*_dev.cuh) and run on the fiber SIMT
 // runtime (simt.h).  Lets the transcription of a kernel be checked against the oracle without a
 // GPU (tests/test_emu_kernels.py).  Test infrastructure only; nothing here is shipped.
+#define SIMT_IMPLEMENTATION
 #include <cuda_runtime.h>  // the shim in tests/emu/shim
 
 std::atomic<long long> g_dfx_launches{0};

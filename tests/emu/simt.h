@@ -10,6 +10,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <functional>
+#include <mutex>
 #include <vector>
 
 // Context switch.  glibc's swapcontext saves/restores the signal mask with a system call on every
@@ -17,6 +18,7 @@
 // dozen instructions that swap the callee-saved registers and the stack pointer do the same job.
 #if defined(__x86_64__)
 extern "C" void simt_switch(void** save_sp, void* load_sp);
+#ifdef SIMT_IMPLEMENTATION  // exactly one translation unit of a binary defines it
 asm(R"(
 .text
 .globl simt_switch
@@ -39,6 +41,7 @@ simt_switch:
     ret
 .size simt_switch,.-simt_switch
 )");
+#endif
 #else
 #error "tests/emu/simt.h: only x86-64 is supported (tests/test_emu_kernels.py skips elsewhere)"
 #endif
@@ -173,8 +176,24 @@ inline void fiber_entry() {
 
 // run `kernel` (a closure over the kernel arguments) on grid x block threads, dyn_bytes of
 // dynamic shared memory per CTA.  CTAs run one after the other.
+inline uint64_t g_default_seed = 0;  // scheduling order of launches that do not pass a seed
+inline void launch3(unsigned gx, unsigned gy, unsigned block, size_t dyn_bytes, std::function<void()> kernel);
 inline void launch(unsigned grid, unsigned block, size_t dyn_bytes, std::function<void()> kernel, uint64_t seed = 0) {
+    const uint64_t keep = g_default_seed;
+    g_default_seed = seed;
+    launch3(grid, 1, block, dyn_bytes, kernel);
+    g_default_seed = keep;
+}
+inline std::mutex& launch_mutex() {
+    static std::mutex m;
+    return m;
+}
+inline void launch3(unsigned gx, unsigned gy, unsigned block, size_t dyn_bytes, std::function<void()> kernel) {
+    // one emulated device: launches from different host threads run one after the other
+    std::lock_guard<std::mutex> lk(launch_mutex());
     State& s = S();
+    const unsigned grid = gx * gy;
+    const uint64_t seed = g_default_seed;
     if (block % 32 != 0 || block == 0 || block > 1024) {
         fprintf(stderr, "simt: block size %u must be a multiple of 32\n", block);
         abort();
@@ -184,10 +203,10 @@ inline void launch(unsigned grid, unsigned block, size_t dyn_bytes, std::functio
     s.nthreads = (int)block;
     s.rng = seed;
     g_bdim = {block, 1, 1};
-    g_gdim = {grid, 1, 1};
+    g_gdim = {gx, gy, 1};
     s.stacks.resize((size_t)block * STACK);
     for (unsigned b = 0; b < grid; b++) {
-        g_block = {b, 0, 0};
+        g_block = {b % gx, b / gx, 0};
         // filled with a pattern (reads of unwritten shared memory show up as garbage); the slack
         // behind the requested size is poisoned for AddressSanitizer, so that any access past the
         // end of the dynamic shared memory aborts (the buffer itself is reused: no reallocation)

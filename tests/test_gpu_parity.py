@@ -13,6 +13,13 @@ from tests.conftest import clustered
 pytestmark = pytest.mark.gpu
 
 IP, L2 = 0, 1
+# DFX_EMU_LIB: the same tests against the library built for the CPU emulator (tests/emu/); the two
+# layout tests shrink their shard there (a fiber-emulated k-means over 30 k vectors takes minutes)
+EMU = bool(__import__("os").environ.get("DFX_EMU_LIB"))
+
+
+def _sz(full, emu):
+    return emu if EMU else full
 
 
 def _engine():
@@ -375,14 +382,16 @@ def test_interleaved_and_row_major_pq_layouts_agree():
 
     E = _engine()
     rs = np.random.RandomState(14)
-    d, nlist, M, n = 128, 48, 32, 30_011            # odd sizes: partial blocks in most lists
+    d, nlist, M, n = 128, _sz(48, 12), 32, _sz(30_011, 3_011)   # odd sizes: partial blocks in most lists
     xb = clustered(rs, n, d, ncl=60)
     xq = xb[:37] + 0.01 * rs.randn(37, d).astype(np.float32)
     g = E.GpuIndex(E.KIND_IVF_PQ, d, L2, nlist=nlist, pq_m=M)
-    g.train(xb[:8000])
-    g.add(xb[:10_000]); g.nprobe = 6
+    if EMU:
+        g.set_param("kmeans_niter", 3)
+    g.train(xb[:_sz(8000, 1500)])
+    g.add(xb[:_sz(10_000, n // 3)]); g.nprobe = 6
     D0, I0 = g.search(xq, 10)                        # builds the interleaved form
-    g.add(xb[10_000:])                               # incremental add on top of it
+    g.add(xb[_sz(10_000, n // 3):])                  # incremental add on top of it
     o = O.OracleIVFPQ(d, nlist, M, 8, coarse_metric=L2)
     o.set_state(g.get_state())                       # export de-interleaves
     assert o.ntotal == n
@@ -391,7 +400,7 @@ def test_interleaved_and_row_major_pq_layouts_agree():
         Do, Io = o.search(xq, k)
         g.set_param("interleaved", 1)
         _assert_same(*g.search(xq, k), Do, Io, f"interleaved nprobe={nprobe}")
-        ids = np.array([0, 5, n - 1, -1, 12345], dtype=np.int64)
+        ids = np.array([0, 5, n - 1, -1, _sz(12345, n // 2 + 7)], dtype=np.int64)
         R_il = g.reconstruct_rows(ids)
         g.set_param("interleaved", 0)
         _assert_same(*g.search(xq, k), Do, Io, f"row-major nprobe={nprobe}")
@@ -415,22 +424,24 @@ def test_scan_variant_2_matches_oracle():
 
     E = _engine()
     rs = np.random.RandomState(21)
-    d, nlist, M, n = 128, 48, 32, 30_011
+    d, nlist, M, n = 128, _sz(48, 12), 32, _sz(30_011, 3_011)
     xb = clustered(rs, n, d, ncl=60)
     xb[-500:] = xb[:500]                             # exact duplicates: ties decided by the id
     xq = xb[:37] + 0.01 * rs.randn(37, d).astype(np.float32)
     xq[:5] = xb[:5]
     g = E.GpuIndex(E.KIND_IVF_PQ, d, L2, nlist=nlist, pq_m=M)
     g.set_param("scan_variant", 2)
-    g.train(xb[:8000])
-    g.add(xb[:10_000]); g.nprobe = 6
+    if EMU:
+        g.set_param("kmeans_niter", 3)
+    g.train(xb[:_sz(8000, 1500)])
+    g.add(xb[:_sz(10_000, n // 3)]); g.nprobe = 6
     g.search(xq, 10)                                 # builds layout 2
-    g.add(xb[10_000:])                               # incremental add on top of it
+    g.add(xb[_sz(10_000, n // 3):])                  # incremental add on top of it
     o = O.OracleIVFPQ(d, nlist, M, 8, coarse_metric=L2)
     o.set_state(g.get_state())
     assert o.ntotal == n
-    ids = np.array([0, 5, n - 1, -1, 12345], dtype=np.int64)
-    for nprobe, k in ((6, 10), (nlist, 32), (1, 1), (17, 7), (nlist, 100), (8, 300)):
+    ids = np.array([0, 5, n - 1, -1, _sz(12345, n // 2 + 7)], dtype=np.int64)
+    for nprobe, k in ((6, 10), (nlist, 32), (1, 1), (_sz(17, 7), 7), (nlist, 100), (8, 300)):
         g.nprobe = nprobe; o.nprobe = nprobe
         Do, Io = o.search(xq, k)
         g.set_param("scan_variant", 2)
