@@ -38,8 +38,7 @@
 #include "dfx_topk.cuh"
 #include "dfx_ptx.cuh"
 
-constexpr int IL2_THREADS = 256;
-constexpr int IL2_NW = IL2_THREADS / 32;
+constexpr int IL2_THREADS = 256;             // default CTA size (DFX_IL2_THREADS: 384 = 2 CTAs/SM of 12 warps)
 constexpr int IL2_LUT_BYTES = 256 * 64 * 4;  // wide table of one query
 constexpr int IL2_QCAP = 64;                 // queue slots per warp (register top-k path)
 constexpr int IL2_MAXG = 16;                 // probes per CTA (choose_group caps G at 16)
@@ -117,8 +116,9 @@ __device__ __noinline__ Il2Flushed il2_flush(uint64_t kept, uint64_t* queue, int
 
 // lutW: [nq][256][64] (wide transposed table, pq_prep_kernel mode 2)
 // REG: k <= 32, register-resident top-k;  !REG: WarpTopK buffers in shared memory (any k)
-template <bool REG>
-__global__ void __launch_bounds__(IL2_THREADS, 3)
+// THREADS: 256 (3 CTAs/SM) or 384 (2 CTAs/SM): 24 warps/SM either way, 3 vs 2 tables per SM
+template <bool REG, int THREADS = IL2_THREADS>
+__global__ void __launch_bounds__(THREADS, THREADS == 256 ? 3 : 2)
 scan_pq_il2_kernel(const float* __restrict__ lutW, const float* __restrict__ dis0, const int32_t* __restrict__ keys,
                    int nprobe, int G, int ngroups, const int64_t* __restrict__ blk_off,
                    const uint4* __restrict__ il_codes, const float* __restrict__ il_tvals,
@@ -131,6 +131,7 @@ scan_pq_il2_kernel(const float* __restrict__ lutW, const float* __restrict__ dis
     __shared__ int s_lb[IL2_MAXG], s_le[IL2_MAXG];  // first / end block of each probed list
     __shared__ float s_ld0[IL2_MAXG];               // |q - c|^2 of each probed list
 
+    constexpr int IL2_NW = THREADS / 32;
     const int64_t q = blockIdx.x / ngroups;
     const int g = blockIdx.x % ngroups;
     const int tid = threadIdx.x, lane = tid & 31;
@@ -291,7 +292,7 @@ scan_pq_il2_kernel(const float* __restrict__ lutW, const float* __restrict__ dis
             if (lane < k) out[lane] = kept;
         }
     } else {
-        cta_merge_and_write<IL2_THREADS>(wt, s_buf, cap, k, out);
+        cta_merge_and_write<THREADS>(wt, s_buf, cap, k, out);
     }
 }
 

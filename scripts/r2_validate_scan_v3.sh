@@ -18,6 +18,8 @@ timeout 600 python bench.py --steps 20 --warmup 3 > gpurun_out/r2_bench_v2.json 
 tail -c 2000 gpurun_out/r2_bench_v2.json
 DFX_SCAN_VARIANT=2 timeout 600 python bench.py --steps 20 --warmup 3 > gpurun_out/r2_bench_v3.json 2> gpurun_out/r2_bench_v3.err
 tail -c 2000 gpurun_out/r2_bench_v3.json
+DFX_SCAN_VARIANT=2 DFX_IL2_THREADS=384 timeout 600 python bench.py --steps 20 --warmup 3 > gpurun_out/r2_bench_v3_384.json 2> gpurun_out/r2_bench_v3_384.err
+tail -c 2000 gpurun_out/r2_bench_v3_384.json
 DFX_SCAN_VARIANT=3 timeout 600 python bench.py --steps 20 --warmup 3 > gpurun_out/r2_bench_v2split.json 2> gpurun_out/r2_bench_v2split.err
 tail -c 2000 gpurun_out/r2_bench_v2split.json
 DFX_SCAN_VARIANT=2 DFX_PREP_VARIANT=2 timeout 600 python bench.py --steps 20 --warmup 3 > gpurun_out/r2_bench_v3_prep2.json 2> gpurun_out/r2_bench_v3_prep2.err

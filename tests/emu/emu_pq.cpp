@@ -81,7 +81,7 @@ int emu_scan_v3(const float* lutW, const float* dis0, const int32_t* keys, int64
                 int cap, uint64_t* part) {
     if (G > IL2_MAXG) return 1;
     const bool reg = k <= 32;
-    const size_t smem = (size_t)IL2_LUT_BYTES + (reg ? (size_t)IL2_NW * IL2_QCAP * 8 : (size_t)IL2_NW * cap * 8);
+    const size_t smem = (size_t)IL2_LUT_BYTES + (reg ? (size_t)(IL2_THREADS / 32) * IL2_QCAP * 8 : (size_t)(IL2_THREADS / 32) * cap * 8);
     const uint4* c4 = reinterpret_cast<const uint4*>(il_codes);
     if (reg)
         simt::launch((unsigned)(nq * ngroups), IL2_THREADS, smem, [=] {
