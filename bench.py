@@ -266,6 +266,9 @@ def main():
     ap.add_argument("--cpu-queries", type=int, default=512)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--sweep", action="store_true", help="also time batch sizes 1, 64, 512")
+    ap.add_argument("--variant-sweep", action="store_true",
+                    help="also time the experimental kernel variants on the already built shards "
+                         "(scan_variant 2 / 3, prep_variant 2) and check that they return the same ids")
     args = ap.parse_args()
 
     import torch
@@ -442,6 +445,32 @@ def main():
             t = timed(bb, st, args.warmup)
             sweep[str(b)] = st * b / (t / 1e3)
 
+    variants = {}
+    if args.variant_sweep:
+        # experimental kernels on the same shards: convert the block layout in place, time the same
+        # batches, compare the ids of one batch with the default kernels' (they must be identical)
+        ref_D, ref_I = group.search(batches[0], K)
+        ref_I = ref_I.clone()
+        for label, sv, pv in (("scan2", 2, 1), ("scan2+prep2", 2, 2), ("scan3", 3, 1), ("default", 1, 1)):
+            for sh in shards:
+                sh.set_param("scan_variant", sv)
+                sh.set_param("prep_variant", pv)
+            _, I_v = group.search(batches[0], K)
+            same = bool(torch.equal(I_v, ref_I))
+            for sh in shards:
+                sh.profile(True)
+                sh.profile_read(reset=True)
+            t = timed(batches, args.steps, args.warmup)
+            sm, sn = 0.0, 0
+            for sh in shards:
+                m_, n_ = sh.profile_read(reset=True)
+                sm += m_
+                sn += n_
+                sh.profile(False)
+            variants[label] = {"qps": args.steps * B / (t / 1e3), "ms_per_step": t / args.steps,
+                               "scan_ms_per_launch": sm / max(sn, 1), "ids_equal_default": same}
+            log(f"variant {label}: {variants[label]}")
+
     # roofline of the dominant kernel (scan_pq): algorithmic bytes = ndis * code_bytes
     peaks = {}
     try:
@@ -506,6 +535,8 @@ def main():
         }
         if sweep:
             out["config"]["qps_by_batch"] = sweep
+        if variants:
+            out["config"]["experimental_variants"] = variants
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.barrier()

@@ -13,17 +13,12 @@ if ! grep -q " passed" gpurun_out/r2_v3_parity.log || grep -q "failed" gpurun_ou
 fi
 echo "== whole gpu suite with variant 2 as the default layout of every new IVF-PQ index"
 DFX_SCAN_VARIANT=2 DFX_EXPERIMENTAL=1 timeout 900 python -m pytest tests -m gpu -q -x 2>&1 | tail -5 | tee gpurun_out/r2_v3_suite.log
-echo "== bench, default variant then variant 2 (same box, back to back)"
-timeout 600 python bench.py --steps 20 --warmup 3 > gpurun_out/r2_bench_v2.json 2> gpurun_out/r2_bench_v2.err
-tail -c 2000 gpurun_out/r2_bench_v2.json
-DFX_SCAN_VARIANT=2 timeout 600 python bench.py --steps 20 --warmup 3 > gpurun_out/r2_bench_v3.json 2> gpurun_out/r2_bench_v3.err
-tail -c 2000 gpurun_out/r2_bench_v3.json
+echo "== bench: default kernels, then every experimental variant on the SAME built shards (one 1B build)"
+timeout 1200 python bench.py --steps 20 --warmup 3 --variant-sweep > gpurun_out/r2_bench_variants.json 2> gpurun_out/r2_bench_variants.err
+tail -c 3000 gpurun_out/r2_bench_variants.json
+echo "== the 12-warp CTA shape of scan 2 needs its own process (read once from the environment)"
 DFX_SCAN_VARIANT=2 DFX_IL2_THREADS=384 timeout 600 python bench.py --steps 20 --warmup 3 > gpurun_out/r2_bench_v3_384.json 2> gpurun_out/r2_bench_v3_384.err
-tail -c 2000 gpurun_out/r2_bench_v3_384.json
-DFX_SCAN_VARIANT=3 timeout 600 python bench.py --steps 20 --warmup 3 > gpurun_out/r2_bench_v2split.json 2> gpurun_out/r2_bench_v2split.err
-tail -c 2000 gpurun_out/r2_bench_v2split.json
-DFX_SCAN_VARIANT=2 DFX_PREP_VARIANT=2 timeout 600 python bench.py --steps 20 --warmup 3 > gpurun_out/r2_bench_v3_prep2.json 2> gpurun_out/r2_bench_v3_prep2.err
-tail -c 2000 gpurun_out/r2_bench_v3_prep2.json
+tail -c 1500 gpurun_out/r2_bench_v3_384.json
 echo "== ncu: one full capture of the new scan kernel (bench.py opens the profiler window around the timed region)"
 DFX_SCAN_VARIANT=2 timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:scan_pq_il2 -c 2 \
     -o gpurun_out/r2_scan_pq_il2 python bench.py --steps 1 --warmup 1 > gpurun_out/r2_ncu.log 2>&1
