@@ -6,6 +6,12 @@ so the drivers take their FFMA paths.  Test infrastructure: nothing in the produ
 
     python tests/emu/build_emu_lib.py          # prints the path of the library
     DFX_EMU_LIB=$(python tests/emu/build_emu_lib.py) python -m pytest tests -m gpu -k "<small cases>"
+
+With --asan the library is instrumented by AddressSanitizer: "device memory" is malloc'ed host
+memory in this build, so an out-of-bounds global or shared access of any kernel, or of the host
+drivers, aborts the test -- the CPU stand-in for `compute-sanitizer --tool memcheck`:
+    LD_PRELOAD=$(g++ -print-file-name=libasan.so) ASAN_OPTIONS=detect_leaks=0:detect_stack_use_after_return=0 \
+    DFX_EMU_LIB=$(python tests/emu/build_emu_lib.py --asan) python -m pytest tests -m gpu -k "<small cases>"
 """
 import os
 import shutil
@@ -30,20 +36,23 @@ def _deps():
     return d
 
 
-def build(verbose=False):
+def build(verbose=False, asan=False):
     cxx = shutil.which("g++")
     if cxx is None:
         raise RuntimeError("g++ not available")
-    os.makedirs(OUT_DIR, exist_ok=True)
+    out_dir = OUT_DIR + ("_asan" if asan else "")
+    lib = LIB.replace(".so", "_asan.so") if asan else LIB
+    flags = FLAGS + (["-fsanitize=address", "-fno-omit-frame-pointer"] if asan else [])
+    os.makedirs(out_dir, exist_ok=True)
     dep_time = max(os.path.getmtime(p) for p in _deps())
-    objs, relink = [], not os.path.exists(LIB)
+    objs, relink = [], not os.path.exists(lib)
     jobs = []
     for src in SOURCES + ["emu_tc_stub.cpp"]:
         path = os.path.join(CSRC, src) if src.endswith(".cu") else os.path.join(EMU_DIR, src)
-        obj = os.path.join(OUT_DIR, os.path.splitext(src)[0] + ".o")
+        obj = os.path.join(out_dir, os.path.splitext(src)[0] + ".o")
         objs.append(obj)
         if not os.path.exists(obj) or os.path.getmtime(obj) < max(dep_time, os.path.getmtime(path)):
-            cmd = [cxx] + (["-x", "c++"] if src.endswith(".cu") else []) + FLAGS + ["-c", path, "-o", obj]
+            cmd = [cxx] + (["-x", "c++"] if src.endswith(".cu") else []) + flags + ["-c", path, "-o", obj]
             jobs.append(subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
             relink = True
     for j in jobs:
@@ -53,9 +62,9 @@ def build(verbose=False):
         if verbose and out:
             print(out, file=sys.stderr)
     if relink:
-        subprocess.run([cxx, "-shared", "-o", LIB] + objs, check=True)
-    return LIB
+        subprocess.run([cxx, "-shared"] + (["-fsanitize=address"] if asan else []) + ["-o", lib] + objs, check=True)
+    return lib
 
 
 if __name__ == "__main__":
-    print(build(verbose=True))
+    print(build(verbose=True, asan="--asan" in sys.argv[1:]))
