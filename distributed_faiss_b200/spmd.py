@@ -89,6 +89,17 @@ class ShardGroup:
             self._stream_max_nq = int(os.environ.get("DFX_SHARD_STREAMS_MAX_NQ", "1024"))
             n_side = int(os.environ.get("DFX_SHARD_STREAMS", "4"))
             self._streams = [torch.cuda.Stream(device=self.device) for _ in range(max(0, n_side))]
+        # EXPERIMENTAL (DFX_GRAPHS=1, off by default, single rank only): latency-bound batches are
+        # replayed from a CUDA graph captured per (nq, k, maximize) shape -- a batch-1 search over
+        # 8 shards is ~70 short launches whose issue cost dominates.  Graphs are dropped whenever
+        # nprobe changes; do not add to the shards while graphs are alive.
+        self._graphs = {}
+        self._graph_max_nq = 0
+        if self.device.type == "cuda" and isinstance(self.backend, CudaBackend) and self.world == 1:
+            import os
+
+            if os.environ.get("DFX_GRAPHS") == "1":
+                self._graph_max_nq = int(os.environ.get("DFX_GRAPHS_MAX_NQ", "256"))
 
     @property
     def num_shards(self) -> int:
@@ -97,6 +108,7 @@ class ShardGroup:
     def set_nprobe(self, nprobe: int):
         for s in self.shards:
             s.nprobe = nprobe
+        self._graphs.clear()
 
     def get_ntotal(self) -> int:
         n = torch.tensor([sum(s.ntotal for s in self.shards)], dtype=torch.int64, device=self.device)
@@ -111,6 +123,33 @@ class ShardGroup:
         Returns (D [nq,k] float32 ascending -- negated scores when `maximize`, as the reference
         returns them for metric "dot" --, I [nq,k] int64 caller ids, -1 = no result), on device,
         identical on every rank."""
+        if self._graph_max_nq and x_t.is_cuda and x_t.shape[0] <= self._graph_max_nq:
+            return self._search_graphed(x_t, k, maximize)
+        return self._search_eager(x_t, k, maximize, src)
+
+    def _search_graphed(self, x_t, k, maximize):
+        key = (tuple(x_t.shape), int(k), bool(maximize))
+        ent = self._graphs.get(key)
+        if ent is None:
+            static_x = x_t.clone()
+            cur = torch.cuda.current_stream(x_t.device)
+            side = torch.cuda.Stream(device=x_t.device)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):  # two eager passes: workspaces reach their final size
+                for _ in range(2):
+                    self._search_eager(static_x, k, maximize, 0)
+            cur.wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                out = self._search_eager(static_x, k, maximize, 0)
+            ent = (graph, static_x, out)
+            self._graphs[key] = ent
+        graph, static_x, out = ent
+        static_x.copy_(x_t)
+        graph.replay()
+        return out[0].clone(), out[1].clone()
+
+    def _search_eager(self, x_t: torch.Tensor, k: int, maximize: bool = False, src: int = 0):
         if self.world > 1:
             dist.broadcast(x_t, src=src, group=self.group)
         nq = x_t.shape[0]

@@ -19,6 +19,11 @@ tail -c 3000 gpurun_out/r2_bench_variants.json
 echo "== the 12-warp CTA shape of scan 2 needs its own process (read once from the environment)"
 DFX_SCAN_VARIANT=2 DFX_IL2_THREADS=384 timeout 600 python bench.py --steps 20 --warmup 3 > gpurun_out/r2_bench_v3_384.json 2> gpurun_out/r2_bench_v3_384.err
 tail -c 1500 gpurun_out/r2_bench_v3_384.json
+echo "== small batches with and without CUDA-graph replay (DFX_GRAPHS=1, experimental)"
+DFX_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_gpu_api.py -m gpu -q -k graph_replay 2>&1 | tail -3 | tee gpurun_out/r2_graphs_parity.log
+timeout 900 python bench.py --steps 20 --warmup 3 --sweep --no-cpu > gpurun_out/r2_bench_sweep_eager.json 2> gpurun_out/r2_bench_sweep_eager.err
+DFX_GRAPHS=1 timeout 900 python bench.py --steps 20 --warmup 3 --sweep --no-cpu > gpurun_out/r2_bench_sweep_graphs.json 2> gpurun_out/r2_bench_sweep_graphs.err
+grep -o '"qps_by_batch": {[^}]*}' gpurun_out/r2_bench_sweep_eager.json gpurun_out/r2_bench_sweep_graphs.json
 echo "== ncu: one full capture of the new scan kernel (bench.py opens the profiler window around the timed region)"
 DFX_SCAN_VARIANT=2 timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:scan_pq_il2 -c 2 \
     -o gpurun_out/r2_scan_pq_il2 python bench.py --steps 1 --warmup 1 > gpurun_out/r2_ncu.log 2>&1

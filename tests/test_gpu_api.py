@@ -171,3 +171,38 @@ def test_shard_group_single_rank_matches_socket_client():
     assert np.array_equal(D_dev.cpu().numpy(), D_ref) and I_dev.cpu().tolist() == meta_ref
     Dh, Ih = group.search_host(xq, k, maximize=True)
     assert np.array_equal(Dh, D_ref) and Ih.tolist() == meta_ref
+
+
+@pytest.mark.skipif(__import__("os").environ.get("DFX_EXPERIMENTAL") != "1",
+                    reason="CUDA-graph replay of small batches has not been validated on hardware yet")
+def test_shard_group_graph_replay_matches_eager(monkeypatch):
+    """DFX_GRAPHS=1: latency-bound batches replayed from a captured graph return the eager results,
+    for fresh inputs and after an nprobe change (IVF-PQ shards, side streams inside the capture)"""
+    import torch
+    from distributed_faiss_b200 import engine, spmd
+
+    rs = np.random.RandomState(5)
+    d, k = 128, 10
+    shards, tables, base = [], [], 0
+    for s in range(3):
+        x = rs.randn(6000, d).astype(np.float32)
+        ix = engine.GpuIndex(engine.KIND_IVF_PQ, d, engine.METRIC_L2, nlist=32, pq_m=32)
+        ix.set_param("kmeans_niter", 5)
+        ix.train(x[:4000])
+        ix.add(x)
+        shards.append(ix)
+        tables.append(torch.arange(base, base + x.shape[0], dtype=torch.int64, device="cuda"))
+        base += x.shape[0]
+    eager = spmd.ShardGroup(shards, tables)
+    monkeypatch.setenv("DFX_GRAPHS", "1")
+    graphed = spmd.ShardGroup(shards, tables)
+    assert graphed._graph_max_nq > 0
+    for nprobe in (4, 9):
+        eager.set_nprobe(nprobe)
+        graphed.set_nprobe(nprobe)
+        for nq in (1, 8, 1, 8):
+            xq = torch.from_numpy(rs.randn(nq, d).astype(np.float32)).cuda()
+            D0, I0 = eager.search(xq, k)
+            D1, I1 = graphed.search(xq, k)
+            assert torch.equal(I0, I1) and torch.equal(D0, D1)
+    assert len(graphed._graphs) == 2
