@@ -12,10 +12,20 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
+def free_ports(n):
+    """n DISTINCT free ports (all sockets are held open until every port is chosen)"""
+    socks = [socket.socket() for _ in range(n)]
+    try:
+        for s in socks:
+            s.bind(("", 0))
+        return [s.getsockname()[1] for s in socks]
+    finally:
+        for s in socks:
+            s.close()
+
+
 def free_port():
-    with socket.socket() as s:
-        s.bind(("", 0))
-        return s.getsockname()[1]
+    return free_ports(1)[0]
 
 
 def wait_listening(ports, timeout=30.0):
@@ -58,13 +68,13 @@ def cluster():
     from distributed_faiss_b200.server import IndexServer
 
     dirs = [tempfile.TemporaryDirectory(), tempfile.TemporaryDirectory()]
-    ports = [free_port() for _ in range(4)]
+    ports = free_ports(5)
+    ports, sp = ports[:4], ports[4]
     servers = []
     for rank, port in enumerate(ports):
         s = IndexServer(rank, dirs[0].name)
         threading.Thread(target=s.start_blocking, args=(port,), daemon=True).start()
         servers.append(s)
-    sp = free_port()
     single = IndexServer(0, dirs[1].name)
     threading.Thread(target=single.start_blocking, args=(sp,), daemon=True).start()
     wait_listening(ports + [sp])

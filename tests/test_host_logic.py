@@ -25,10 +25,20 @@ from tests.oracle_engine import oracle_engine_factory, oracle_merge
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
+def free_ports(n):
+    """n DISTINCT free ports (all sockets are held open until every port is chosen)"""
+    socks = [socket.socket() for _ in range(n)]
+    try:
+        for s in socks:
+            s.bind(("", 0))
+        return [s.getsockname()[1] for s in socks]
+    finally:
+        for s in socks:
+            s.close()
+
+
 def free_port():
-    with socket.socket() as s:
-        s.bind(("", 0))
-        return s.getsockname()[1]
+    return free_ports(1)[0]
 
 
 def rand_meta(n, nchars=5):
@@ -40,13 +50,13 @@ def cluster():
     """4 shard servers + 1 single server on localhost, oracle engines, device merge replaced"""
     ResultHeap.merge_backend = staticmethod(oracle_merge)
     dirs = [tempfile.TemporaryDirectory(), tempfile.TemporaryDirectory()]
-    multi_ports = [free_port() for _ in range(4)]
+    multi_ports = free_ports(5)
+    multi_ports, single_port = multi_ports[:4], multi_ports[4]
     servers = []
     for rank, port in enumerate(multi_ports):
         s = IndexServer(rank, dirs[0].name, engine_factory=oracle_engine_factory)
         threading.Thread(target=s.start_blocking, args=(port,), daemon=True).start()
         servers.append(s)
-    single_port = free_port()
     single = IndexServer(0, dirs[1].name, engine_factory=oracle_engine_factory)
     threading.Thread(target=single.start_blocking, args=(single_port,), daemon=True).start()
     wait_listening(multi_ports + [single_port])
