@@ -24,9 +24,13 @@
 // TMEM accumulator buffers overlap the epilogue of tile i with the MMAs of tile i+1.
 #include "dfx_internal.h"
 #include "dfx_select.cuh"
+#include "dfx_ptx.cuh"
+#ifndef DFX_EMU
 #include <cuda.h>
 #include <cuda_bf16.h>
+#endif
 
+#ifndef DFX_EMU  // tcgen05 / TMA / mbarrier PTX: hardware only (the CPU emulator uses emu_tc_screen below)
 // ------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return (uint32_t)__cvta_generic_to_shared(p);
@@ -114,6 +118,8 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
 // instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=128
 static constexpr uint32_t TC_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
 
+#endif  // !DFX_EMU
+
 // ------------------------------------------------------------------ the kernel
 namespace tc {
 constexpr int TILE = 128;           // rows of A and of B per tile
@@ -131,6 +137,71 @@ struct Smem {
 };
 }  // namespace tc
 
+#ifdef DFX_EMU
+// ---- CPU emulator stand-ins (tests/emu/): the screening kernel cannot be emulated instruction
+// by instruction, so its RESULT is restated: the same bf16 hi/lo split of both operands, the
+// same three partial products, fp32 accumulation (order not specified by the hardware either),
+// and the epilogue's packed (min, runner-up, arg-min) per 32 centroids.  Everything downstream
+// (group selection, exact canonical re-evaluation, the drivers) is the product code.
+struct __nv_bfloat16 { unsigned short x; };
+static inline float emu_bf16_rn(float v) {  // round to nearest even bf16, returned as fp32
+    uint32_t u;
+    memcpy(&u, &v, 4);
+    if ((u & 0x7f800000u) == 0x7f800000u) return v;
+    u += 0x7fffu + ((u >> 16) & 1u);
+    u &= 0xffff0000u;
+    float r;
+    memcpy(&r, &u, 4);
+    return r;
+}
+// "planes" hold a padded fp32 copy in the emulator build (same byte size as the two bf16 planes)
+__global__ void split_bf16_kernel(const float* __restrict__ x, int64_t n, int64_t n_pad, int d,
+                                  __nv_bfloat16* __restrict__ out) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_pad * d) return;
+    reinterpret_cast<float*>(out)[t] = (t / d < n) ? x[t] : 0.f;
+}
+static void emu_tc_screen(const float* q, int64_t nq, const float* c, int64_t nlist, int64_t nl_pad, int d,
+                          const float* cnorm, int metric, float* gmin, float* gmin2, uint8_t* gargc, int ng) {
+    const float big = 3.0e38f;
+    std::vector<float> ch((size_t)nl_pad * d), cl((size_t)nl_pad * d), qh(d), ql(d);
+    for (size_t i = 0; i < ch.size(); i++) {
+        ch[i] = emu_bf16_rn(c[i]);
+        cl[i] = emu_bf16_rn(c[i] - ch[i]);
+    }
+    for (int64_t row = 0; row < nq; row++) {
+        for (int k = 0; k < d; k++) {
+            qh[k] = emu_bf16_rn(q[row * d + k]);
+            ql[k] = emu_bf16_rn(q[row * d + k] - qh[k]);
+        }
+        for (int g = 0; g < ng; g++) {
+            float m1 = big, m2 = big;
+            for (int j = 0; j < 32; j++) {
+                const int64_t col = (int64_t)g * 32 + j;
+                float ip = 0.f;
+                const float* h = &ch[(size_t)col * d];
+                const float* l = &cl[(size_t)col * d];
+                for (int k = 0; k < d; k++) ip += qh[k] * h[k] + ql[k] * h[k] + qh[k] * l[k];
+                float cn = big;
+                if (col < nlist) cn = (metric == DFX_METRIC_L2) ? cnorm[col] : 0.f;
+                const float v = (metric == DFX_METRIC_IP) ? (cn - ip) : fmaf(-2.f, ip, cn);
+                uint32_t u;
+                memcpy(&u, &v, 4);
+                u = (u & ~31u) | (uint32_t)j;
+                float vj;
+                memcpy(&vj, &u, 4);
+                m2 = fminf(m2, fmaxf(m1, vj));
+                m1 = fminf(m1, vj);
+            }
+            uint32_t u1;
+            memcpy(&u1, &m1, 4);
+            gmin[row * ng + g] = m1;
+            gmin2[row * ng + g] = m2;
+            gargc[row * ng + g] = (uint8_t)(u1 & 31u);
+        }
+    }
+}
+#else
 // tmQ: bf16 [2*nq_pad, d]  (rows [0,nq_pad) = hi plane, [nq_pad, 2 nq_pad) = lo plane)
 // tmC: bf16 [2*nl_pad, d]
 // gmin: float [nq][ng], ng = nl_pad/32
@@ -320,6 +391,8 @@ __global__ void split_bf16_kernel(const float* __restrict__ x, int64_t n, int64_
     out[n_pad * d + t] = lo;
 }
 
+#endif  // DFX_EMU
+
 // the G smallest group minima of a row, G <= 8: one warp per row, G rounds of warp arg-min
 template <int G>
 __global__ void topg_small_kernel(const float* __restrict__ gmin, int64_t nq, int ng,
@@ -472,7 +545,7 @@ rerank_kernel(const float* __restrict__ Q, int d, const float* __restrict__ cent
               int ng, float cmax2, uint64_t* __restrict__ out, int32_t* __restrict__ assign,
               const int32_t* __restrict__ rows, const int32_t* __restrict__ nrows_dev, int64_t nrows,
               int32_t* __restrict__ keys) {
-    extern __shared__ __align__(16) unsigned char rr_smem[];
+    DFX_DYN_SMEM(unsigned char, rr_smem, 16);
     float* s_q = reinterpret_cast<float*>(rr_smem);
     uint64_t* s_c = reinterpret_cast<uint64_t*>(rr_smem + ((size_t)d * 4 + 15) / 16 * 16);  // MODE 2
     __shared__ unsigned long long s_best[4];
@@ -581,6 +654,7 @@ __global__ void max_reduce_kernel(const float* __restrict__ x, int64_t n, float*
 }
 
 // ------------------------------------------------------------------ host side
+#ifndef DFX_EMU
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -608,6 +682,8 @@ static void make_tmap(CUtensorMap* tm, const void* base, int64_t rows, int d) {
                                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     DFX_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
 }
+
+#endif  // !DFX_EMU
 
 bool dfx_tc_supported(int d) { return d == 64 || d == 128; }
 
@@ -646,6 +722,11 @@ static void tc_screen(dfx_index* idx, int d, const float* d_x, int64_t nq, const
     idx->tc_q.reserve((size_t)2 * nq_pad * d * 2);
     DFX_LAUNCH(split_bf16_kernel, (unsigned)dfx_ceil_div(nq_pad * d, 256), 256, 0, st, d_x, nq, nq_pad, d,
                idx->tc_q.as<__nv_bfloat16>());
+#ifdef DFX_EMU
+    emu_tc_screen(idx->tc_q.as<float>(), nq, static_cast<const float*>(cent_planes), nlist, nl_pad, d, cnorm, metric,
+                  gmin, gmin2, gargc, ng);
+    return;
+#else
     CUtensorMap tmQ, tmC;
     make_tmap(&tmQ, idx->tc_q.p, 2 * nq_pad, d);
     make_tmap(&tmC, cent_planes, 2 * nl_pad, d);
@@ -688,6 +769,7 @@ static void tc_screen(dfx_index* idx, int d, const float* d_x, int64_t nq, const
     else if (metric == DFX_METRIC_L2) DFX_TC_LAUNCH(1, DFX_METRIC_L2);
     else DFX_TC_LAUNCH(1, DFX_METRIC_IP);
 #undef DFX_TC_LAUNCH
+#endif  // DFX_EMU
 }
 
 // top-nprobe lists per query -> keys int32 [nq, nprobe] (exactly the oracle's coarse result)

@@ -1,8 +1,8 @@
 """Build libdfx_emu_full.so: the WHOLE C-ABI library (include/dfx.h) compiled by g++ from the
 product sources (distributed_faiss_b200/csrc/*.cu with -DDFX_EMU) on top of the fiber SIMT runtime
 (simt.h) and the CUDA stand-in headers (shim/).  Kernels run one CTA after the other on the CPU;
-the tcgen05 coarse quantizer is replaced by a stub that reports "not supported" (emu_tc_stub.cpp),
-so the drivers take their FFMA paths.  Test infrastructure: nothing in the product loads this file.
+the tcgen05 screening kernel of the coarse quantizer is replaced by a plain C++ restatement of its
+result (dfx_tc.cu, DFX_EMU branch); group selection, exact re-evaluation and the drivers are the product code.  Test infrastructure: nothing in the product loads this file.
 
     python tests/emu/build_emu_lib.py          # prints the path of the library
     DFX_EMU_LIB=$(python tests/emu/build_emu_lib.py) python -m pytest tests -m gpu -k "<small cases>"
@@ -23,7 +23,7 @@ ROOT = os.path.dirname(os.path.dirname(EMU_DIR))
 CSRC = os.path.join(ROOT, "distributed_faiss_b200", "csrc")
 OUT_DIR = os.path.join(EMU_DIR, "_build", "lib")
 LIB = os.path.join(EMU_DIR, "_build", "libdfx_emu_full.so")
-SOURCES = ["dfx_api.cu", "dfx_search.cu", "dfx_build.cu", "dfx_scan_il.cu", "dfx_scan_il2.cu"]
+SOURCES = ["dfx_api.cu", "dfx_search.cu", "dfx_build.cu", "dfx_scan_il.cu", "dfx_scan_il2.cu", "dfx_tc.cu"]
 FLAGS = ["-std=c++17", "-O1", "-g", "-fPIC", "-ffp-contract=off", "-DDFX_EMU", "-Wno-unknown-pragmas",
          "-Wno-attributes", "-I", os.path.join(EMU_DIR, "shim"), "-I", CSRC]
 
@@ -47,7 +47,7 @@ def build(verbose=False, asan=False):
     dep_time = max(os.path.getmtime(p) for p in _deps())
     objs, relink = [], not os.path.exists(lib)
     jobs = []
-    for src in SOURCES + ["emu_tc_stub.cpp"]:
+    for src in SOURCES + ["emu_simt_impl.cpp"]:
         path = os.path.join(CSRC, src) if src.endswith(".cu") else os.path.join(EMU_DIR, src)
         obj = os.path.join(out_dir, os.path.splitext(src)[0] + ".o")
         objs.append(obj)

@@ -3,8 +3,9 @@
 runtime, and a subset of the `gpu` parity tests is run against that build in a subprocess
 (DFX_EMU_LIB, see tests/conftest.py).  This is how host-side changes and the experimental kernel
 variants (scan_variant 2 / 3, prep_variant 2) are checked in a container without a GPU: same
-sources, same tests, same oracle; only the PTX primitives (dfx_ptx.cuh) and the tcgen05 coarse
-quantizer (stubbed out: the drivers take the FFMA paths) are not what runs on hardware.
+sources, same tests, same oracle; only the PTX primitives (dfx_ptx.cuh) and the tcgen05 screening
+kernel (its result is restated in C++; everything around it is the product code) are not what runs
+on hardware.
 
 The full `-m gpu` suite also passes this way but takes tens of minutes; the subset below is sized
 for the regular CPU run.  Run everything with:
@@ -34,6 +35,9 @@ SUBSET = [
     "tests/test_gpu_parity.py::test_scan_variant_2_matches_oracle",   # scan_variant 1/2/3, prep_variant 2
     "tests/test_gpu_api.py::test_sharded_equals_unsharded_exactly",   # servers + client over the C-ABI
     "tests/test_gpu_api.py::test_result_aggregation_on_device",
+    # coarse quantizer through the tensor-core path: screening restated in C++ (dfx_tc.cu, DFX_EMU),
+    # group selection + exact re-rank + drivers are the product code
+    "tests/test_gpu_parity.py::test_tensor_core_coarse_quantizer_matches_oracle[ivf_flat-1-64-0]",
 ]
 
 

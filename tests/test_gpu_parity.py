@@ -101,6 +101,8 @@ def _build_both(kind, metric, d, nlist, M, n, rs, via="gpu"):
     xb = clustered(rs, n, d, ncl=max(8, nlist // 2))
     g, o = _mk_pair(kind, d, metric, nlist=nlist, M=M)
     if via == "gpu":
+        if EMU and kind != "flat":
+            g.set_param("kmeans_niter", 2)
         g.train(xb[: n // 2])
         g.add(xb[: n // 3]); g.add(xb[n // 3:])
         st = g.get_state()
@@ -331,7 +333,7 @@ def test_tensor_core_coarse_quantizer_matches_oracle(kind, metric, d, M):
     screening) + canonical fp32 re-rank: probe lists, hence results, must still be bit-identical
     to the oracle's, and identical to the plain FFMA path."""
     rs = np.random.RandomState(12)
-    nlist, n = 1024, 60_000
+    nlist, n = 1024, _sz(60_000, 6_000)
     g, o, xb = _build_both(kind, metric, d, nlist, M, n, rs, via="gpu")
     xq = np.concatenate([clustered(rs, 150, d, ncl=64), xb[:50] + 0.01 * rs.randn(50, d).astype(np.float32)])
     for nprobe in (1, 7, 64):
@@ -359,11 +361,11 @@ def test_tensor_core_assign_matches_oracle():
 
     E = _engine()
     rs = np.random.RandomState(13)
-    d, nlist, M, n = 128, 1024, 32, 80_000
+    d, nlist, M, n = 128, 1024, 32, _sz(80_000, 6_000)
     xb = clustered(rs, n, d, ncl=700, sigma=0.5)
     g = E.GpuIndex(E.KIND_IVF_PQ, d, L2, nlist=nlist, pq_m=M)
-    g.set_param("kmeans_niter", 6)
-    g.train(xb[:40000])
+    g.set_param("kmeans_niter", _sz(6, 2))
+    g.train(xb[:_sz(40000, 3000)])
     g.add(xb)
     st = g.get_state()
     o = O.OracleIVFPQ(d, nlist, M, 8, coarse_metric=L2)
