@@ -83,6 +83,8 @@ int dfx_create(const dfx_cfg* cfg, dfx_index** out) {
         if (const char* e = getenv("DFX_PREP_VARIANT"))
             if (atoi(e) == 2) idx->prep_variant = 2;
     }
+    if (const char* e = getenv("DFX_RERANK_VARIANT"))
+        if (atoi(e) == 2) idx->rerank_variant = 2;
     DeviceGuard g(cfg->device);
     DFX_CUDA(cudaStreamCreateWithFlags(&idx->stream, cudaStreamNonBlocking));
     *out = idx.release();
@@ -119,6 +121,10 @@ int dfx_set_param(dfx_index* idx, const char* name, double value) {
         idx->il_enabled = value != 0;
         if (!idx->il_enabled) dfx_pq_il_to_rm(idx, idx->stream);
         else if (idx->trained && idx->n_pending == 0 && idx->n_sorted > 0) dfx_pq_rm_to_il(idx, idx->stream);
+    }
+    else if (n == "rerank_variant") {
+        DFX_REQUIRE(value == 1 || value == 2, "rerank_variant must be 1 or 2");
+        idx->rerank_variant = (int)value;
     }
     else if (n == "prep_variant") {
         DFX_REQUIRE(value == 1 || value == 2, "prep_variant must be 1 or 2");

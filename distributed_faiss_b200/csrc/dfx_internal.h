@@ -55,6 +55,7 @@ struct dfx_index {
     float tc_cmax2 = 0.f;
     bool tc_ready = false;
     bool tc_enabled = true;
+    int rerank_variant = 1;  // 2 = rerank2_kernel (warp per query; dfx_set_param "rerank_variant")
 
     // scan-kernel profiling (dfx_profile_enable)
     bool prof_on = false;

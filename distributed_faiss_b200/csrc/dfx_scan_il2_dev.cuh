@@ -43,37 +43,6 @@ constexpr int IL2_LUT_BYTES = 256 * 64 * 4;  // wide table of one query
 constexpr int IL2_QCAP = 64;                 // queue slots per warp (register top-k path)
 constexpr int IL2_MAXG = 16;                 // probes per CTA (choose_group caps G at 16)
 
-// ascending bitonic sort of one 64-bit value per lane
-__device__ __forceinline__ uint64_t il2_sort32_asc(uint64_t x, int lane) {
-#pragma unroll
-    for (int size = 2; size <= 32; size <<= 1) {
-#pragma unroll
-        for (int stride = size >> 1; stride >= 1; stride >>= 1) {
-            const uint64_t o = __shfl_xor_sync(0xffffffffu, x, stride);
-            const bool up = (lane & size) == 0;  // size == 32: true for every lane
-            const bool lower = (lane & stride) == 0;
-            const uint64_t mn = x < o ? x : o, mx = x < o ? o : x;
-            x = (lower == up) ? mn : mx;
-        }
-    }
-    return x;
-}
-// kept, x_asc: ascending over lanes.  returns the 32 smallest of their union, ascending.
-// (element-wise min of an ascending and a descending sequence is bitonic and holds the 32
-// smallest; five half-cleaner stages sort it)
-__device__ __forceinline__ uint64_t il2_merge_sorted(uint64_t kept, uint64_t x_asc, int lane) {
-    const uint64_t xr = __shfl_sync(0xffffffffu, x_asc, 31 - lane);
-    uint64_t y = kept < xr ? kept : xr;
-#pragma unroll
-    for (int stride = 16; stride >= 1; stride >>= 1) {
-        const uint64_t o = __shfl_xor_sync(0xffffffffu, y, stride);
-        const bool lower = (lane & stride) == 0;
-        const uint64_t mn = y < o ? y : o, mx = y < o ? o : y;
-        y = lower ? mn : mx;
-    }
-    return y;
-}
-
 // Merge the first min(cnt, 32) entries of a warp's queue (key << 32 | position) into its
 // register-resident set and move the rest to the front of the queue; the ids of the merged
 // positions are gathered here.  Returns the new set, the new count and, once k candidates are held,
@@ -99,7 +68,7 @@ __device__ __noinline__ Il2Flushed il2_flush(uint64_t kept, uint64_t* queue, int
     __syncwarp();  // queue fully read before it is rewritten
     if (lane < rest) queue[lane] = moved;
     __syncwarp();
-    kept = il2_merge_sorted(kept, il2_sort32_asc(x, lane), lane);
+    kept = dfx_warp_merge_sorted32(kept, dfx_warp_sort32_asc(x, lane), lane);
     const uint64_t kth = __shfl_sync(0xffffffffu, kept, k - 1);
     if (kth != DFX_COMP_NONE) {
         thr = dfx_key2f((uint32_t)(kth >> 32));
@@ -288,7 +257,7 @@ scan_pq_il2_kernel(const float* __restrict__ lutW, const float* __restrict__ dis
         __syncthreads();
         if (warp == 0) {
 #pragma unroll 1
-            for (int w2 = 1; w2 < IL2_NW; w2++) kept = il2_merge_sorted(kept, s_buf[w2 * 32 + lane], lane);
+            for (int w2 = 1; w2 < IL2_NW; w2++) kept = dfx_warp_merge_sorted32(kept, s_buf[w2 * 32 + lane], lane);
             if (lane < k) out[lane] = kept;
         }
     } else {

@@ -24,6 +24,7 @@
 // TMEM accumulator buffers overlap the epilogue of tile i with the MMAs of tile i+1.
 #include "dfx_internal.h"
 #include "dfx_select.cuh"
+#include "dfx_topk.cuh"
 #include "dfx_ptx.cuh"
 #ifndef DFX_EMU
 #include <cuda.h>
@@ -623,6 +624,96 @@ rerank_kernel(const float* __restrict__ Q, int d, const float* __restrict__ cent
     }
 }
 
+// EXPERIMENTAL (dfx_set_param "rerank_variant" = 2, off by default; search path, nprobe <= 32,
+// G <= 64): the same decision as rerank_kernel<2>, one WARP per query instead of one 128-thread
+// CTA.  rerank_kernel<2> costs 62 us per 4096-query launch although only ~9 candidates per query
+// survive the screening: one thread sums |q|^2 serially, 128 threads walk 512 candidate slots of
+// which a handful are live, then a block-wide sort.  Here: lanes own the selected groups, live
+// candidates are compacted into a per-warp list (arg-min column, or all 32 columns of a group
+// whose runner-up is within the tolerance), each lane evaluates one candidate in the canonical
+// seq-k order, and the nprobe smallest come out of a register bitonic network.  The candidate set
+// is a superset of the true top-nprobe for any tolerance >= the screening error, so the keys are
+// identical to rerank_kernel<2>'s (|q|^2 is summed in a different order: only the tolerance moves,
+// by one ulp).
+constexpr int RR2_WARPS = 4;
+__global__ void __launch_bounds__(RR2_WARPS * 32)
+rerank2_kernel(const float* __restrict__ Q, int d, const float* __restrict__ cent, const float* __restrict__ cnorm,
+               int64_t nlist, int metric, const int32_t* __restrict__ groups, int G, int nprobe,
+               const float* __restrict__ gmin, const float* __restrict__ gmin2, const uint8_t* __restrict__ gargc,
+               int ng, float cmax2, int64_t nrows, int32_t* __restrict__ keys) {
+    DFX_DYN_SMEM(unsigned char, rr2_smem, 16);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * RR2_WARPS + warp;
+    if (row >= nrows) return;  // whole warps leave; no block-wide barrier below
+    const int dq = (d + 3) / 4 * 4;
+    float* s_q = reinterpret_cast<float*>(rr2_smem) + (size_t)warp * dq;
+    int32_t* s_cand = reinterpret_cast<int32_t*>(rr2_smem + (size_t)RR2_WARPS * dq * 4) + (size_t)warp * G * 32;
+    float part = 0.f;
+    for (int i = lane; i < d; i += 32) {
+        const float v = Q[row * d + i];
+        s_q[i] = v;
+        part = __fmaf_rn(v, v, part);
+    }
+    const float qn2 = dfx_warp_butterfly(part);
+    __syncwarp();
+    const int gk = (nprobe <= G) ? groups[row * G + nprobe - 1] : -1;
+    const float thr = (gk >= 0 ? gmin[row * ng + gk] : __int_as_float(0x7f800000)) + screen_tol(qn2, cmax2);
+    // ---- candidate list: one entry for a live group's arg-min column, 32 for an expanded group
+    int cnt = 0;
+    for (int g0 = 0; g0 < G; g0 += 32) {
+        const int gi = g0 + lane;
+        int gid = -1;
+        bool live = false, expand = false;
+        int argc = 0;
+        if (gi < G) {
+            gid = groups[row * G + gi];
+            if (gid >= 0) {
+                const int64_t o = row * ng + gid;
+                live = gmin[o] <= thr;
+                expand = live && gmin2[o] <= thr;
+                argc = (int)gargc[o];
+            }
+        }
+        const bool single = live && !expand && ((int64_t)gid * 32 + argc) < nlist;
+        const unsigned ms = __ballot_sync(0xffffffffu, single);
+        if (single) s_cand[cnt + __popc(ms & ((1u << lane) - 1u))] = gid * 32 + argc;
+        cnt += __popc(ms);
+        unsigned me = __ballot_sync(0xffffffffu, expand);
+        while (me) {  // rare: a group whose runner-up cannot be ruled out contributes all its columns
+            const int src = __ffs((int)me) - 1;
+            me &= me - 1;
+            const int eg = __shfl_sync(0xffffffffu, gid, src);
+            const int64_t col = (int64_t)eg * 32 + lane;
+            const bool ok = col < nlist;
+            const unsigned mo = __ballot_sync(0xffffffffu, ok);
+            if (ok) s_cand[cnt + __popc(mo & ((1u << lane) - 1u))] = (int32_t)col;
+            cnt += __popc(mo);
+        }
+    }
+    __syncwarp();
+    // ---- exact canonical values, 32 candidates at a time; keep the 32 smallest composites
+    uint64_t kept = DFX_COMP_NONE;
+    for (int c0 = 0; c0 < cnt; c0 += 32) {
+        uint64_t comp = DFX_COMP_NONE;
+        if (c0 + lane < cnt) {
+            const int64_t col = s_cand[c0 + lane];
+            const float* x = cent + col * d;
+            float acc = 0.f;
+            for (int k = 0; k < d; k += 4) {
+                const float4 xv = *reinterpret_cast<const float4*>(x + k);
+                acc = __fmaf_rn(s_q[k + 0], xv.x, acc);
+                acc = __fmaf_rn(s_q[k + 1], xv.y, acc);
+                acc = __fmaf_rn(s_q[k + 2], xv.z, acc);
+                acc = __fmaf_rn(s_q[k + 3], xv.w, acc);
+            }
+            const float v = (metric == DFX_METRIC_IP) ? -acc : __fmaf_rn(-2.f, acc, cnorm[col]);
+            comp = dfx_comp(v, (uint32_t)col);
+        }
+        kept = dfx_warp_merge_sorted32(kept, dfx_warp_sort32_asc(comp, lane), lane);
+    }
+    if (lane < nprobe) keys[row * nprobe + lane] = (kept == DFX_COMP_NONE) ? -1 : (int32_t)(uint32_t)kept;
+}
+
 // assign fast path: one thread per row decides from the screening summary alone when the best
 // group's arg-min column is unambiguous (no other column within tol); other rows are queued
 // for the exact evaluation above.
@@ -799,7 +890,13 @@ void dfx_tc_coarse_search(dfx_index* idx, const float* d_x, int64_t nq, int npro
                                    nullptr, nullptr, 0, st);
         }
         const int P_cand = dfx_next_pow2(G * 32 < 32 ? 32 : G * 32);
-        if (P_cand <= 4096) {  // fused: candidates never leave the SM
+        if (idx->rerank_variant == 2 && nprobe <= 32 && G <= 64 && d % 4 == 0) {  // experimental
+            const size_t smem = (size_t)RR2_WARPS * ((d + 3) / 4 * 4) * 4 + (size_t)RR2_WARPS * G * 32 * 4;
+            DFX_LAUNCH(rerank2_kernel, (unsigned)dfx_ceil_div(qc, RR2_WARPS), RR2_WARPS * 32, smem, st, d_x + q0 * d, d,
+                       idx->centroids.as<float>(), idx->cnorm.as<float>(), nlist, idx->cfg.metric,
+                       idx->tc_groups.as<int32_t>(), G, nprobe, idx->tc_gmin.as<float>(), idx->tc_gmin2.as<float>(),
+                       idx->tc_gargc.as<uint8_t>(), ng, idx->tc_cmax2, qc, keys + q0 * nprobe);
+        } else if (P_cand <= 4096) {  // fused: candidates never leave the SM
             auto kern = rerank_kernel<2>;
             const size_t smem = ((size_t)d * 4 + 15) / 16 * 16 + (size_t)P_cand * 8;
             DFX_LAUNCH(kern, (unsigned)qc, 128, smem, st, d_x + q0 * d, d, idx->centroids.as<float>(),

@@ -130,3 +130,37 @@ __device__ __forceinline__ void cta_merge_and_write(WarpTopK& wt, uint64_t* s_bu
     }
     for (int j = threadIdx.x; j < k; j += THREADS) out[j] = s_buf[j];
 }
+
+// =====================================================================================
+// register-resident variants: one 64-bit composite per lane, bitonic networks over shuffles
+// =====================================================================================
+// ascending bitonic sort of one 64-bit value per lane
+__device__ __forceinline__ uint64_t dfx_warp_sort32_asc(uint64_t x, int lane) {
+#pragma unroll
+    for (int size = 2; size <= 32; size <<= 1) {
+#pragma unroll
+        for (int stride = size >> 1; stride >= 1; stride >>= 1) {
+            const uint64_t o = __shfl_xor_sync(0xffffffffu, x, stride);
+            const bool up = (lane & size) == 0;  // size == 32: true for every lane
+            const bool lower = (lane & stride) == 0;
+            const uint64_t mn = x < o ? x : o, mx = x < o ? o : x;
+            x = (lower == up) ? mn : mx;
+        }
+    }
+    return x;
+}
+// kept, x_asc: ascending over lanes.  returns the 32 smallest of their union, ascending.
+// (element-wise min of an ascending and a descending sequence is bitonic and holds the 32
+// smallest; five half-cleaner stages sort it)
+__device__ __forceinline__ uint64_t dfx_warp_merge_sorted32(uint64_t kept, uint64_t x_asc, int lane) {
+    const uint64_t xr = __shfl_sync(0xffffffffu, x_asc, 31 - lane);
+    uint64_t y = kept < xr ? kept : xr;
+#pragma unroll
+    for (int stride = 16; stride >= 1; stride >>= 1) {
+        const uint64_t o = __shfl_xor_sync(0xffffffffu, y, stride);
+        const bool lower = (lane & stride) == 0;
+        const uint64_t mn = y < o ? y : o, mx = y < o ? o : y;
+        y = lower ? mn : mx;
+    }
+    return y;
+}

@@ -75,7 +75,9 @@ int dfx_add_dev(dfx_index *idx, int64_t n, const float *d_x, void *stream);
  * "scan_variant" (1): 2 selects the experimental lane-per-vector block layout and scan kernel
  * (dfx_scan_il2.cu; same results by construction, not yet validated on hardware), 3 the default
  * kernel on a block layout whose 128-bit loads are contiguous (same status);
- * "prep_variant" (1): 2 selects the experimental table-building kernel pq_prep2_kernel (same) */
+ * "prep_variant" (1): 2 selects the experimental table-building kernel pq_prep2_kernel (same);
+ * "rerank_variant" (1): 2 selects the experimental warp-per-query exact re-rank of the coarse
+ * quantizer's tensor-core path (same) */
 int dfx_set_param(dfx_index *idx, const char *name, double value);
 /* pre-size the shard for n_total vectors (optional; avoids regrowth while bulk loading) */
 int dfx_reserve(dfx_index *idx, int64_t n_total);

@@ -346,6 +346,11 @@ def test_tensor_core_coarse_quantizer_matches_oracle(kind, metric, d, M):
         g.set_param("tensor_cores", 0)
         Df, If = g.search(xq, 10)
         _assert_same(Df, If, Do, Io, f"FFMA coarse {kind} nprobe={nprobe}")
+        if __import__("os").environ.get("DFX_EXPERIMENTAL") == "1":   # warp-per-query re-rank (not yet run on hardware)
+            g.set_param("tensor_cores", 1)
+            g.set_param("rerank_variant", 2)
+            _assert_same(*g.search(xq, 10), Do, Io, f"TC coarse, rerank variant 2, {kind} nprobe={nprobe}")
+            g.set_param("rerank_variant", 1)
     g.set_param("tensor_cores", 1)
     D1, I1 = g.search(xq[3:4], 10)  # single query: a 128-row tile with one valid row
     g.nprobe = 64
