@@ -140,8 +140,17 @@ class ShardGroup:
                     self._search_eager(static_x, k, maximize, 0)
             cur.wait_stream(side)
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                out = self._search_eager(static_x, k, maximize, 0)
+            try:
+                with torch.cuda.graph(graph):
+                    out = self._search_eager(static_x, k, maximize, 0)
+            except RuntimeError as e:  # something in the path is not capturable: stay eager
+                import logging
+
+                logging.getLogger("distributed_faiss_b200").warning("CUDA-graph capture failed, disabled: %s", e)
+                self._graph_max_nq = 0
+                self._graphs.clear()
+                torch.cuda.synchronize(x_t.device)
+                return self._search_eager(x_t, k, maximize, 0)
             ent = (graph, static_x, out)
             self._graphs[key] = ent
         graph, static_x, out = ent
