@@ -85,6 +85,8 @@ int dfx_create(const dfx_cfg* cfg, dfx_index** out) {
     }
     if (const char* e = getenv("DFX_RERANK_VARIANT"))
         if (atoi(e) == 2) idx->rerank_variant = 2;
+    if (const char* e = getenv("DFX_FLAT_TC"))
+        if (atoi(e) == 1) idx->flat_tc = true;
     DeviceGuard g(cfg->device);
     DFX_CUDA(cudaStreamCreateWithFlags(&idx->stream, cudaStreamNonBlocking));
     *out = idx.release();
@@ -122,6 +124,7 @@ int dfx_set_param(dfx_index* idx, const char* name, double value) {
         if (!idx->il_enabled) dfx_pq_il_to_rm(idx, idx->stream);
         else if (idx->trained && idx->n_pending == 0 && idx->n_sorted > 0) dfx_pq_rm_to_il(idx, idx->stream);
     }
+    else if (n == "flat_tensor_cores") idx->flat_tc = value != 0;
     else if (n == "rerank_variant") {
         DFX_REQUIRE(value == 1 || value == 2, "rerank_variant must be 1 or 2");
         idx->rerank_variant = (int)value;
@@ -448,6 +451,7 @@ int dfx_set_array(dfx_index* idx, const char* name, const void* in, int64_t nbyt
         if (idx->cfg.kind == DFX_FLAT) {
             DFX_REQUIRE(nbytes % (d * 4) == 0, "xb: wrong size");
             idx->n_sorted = nbytes / (d * 4);
+            idx->tc_flat_rows = -1;  // imported rows: any bf16 planes are stale
             upload(idx->payload, nbytes);
             if (idx->cfg.metric == DFX_METRIC_L2) {
                 idx->xnorm.reserve((size_t)std::max<int64_t>(idx->n_sorted, 1) * 4);

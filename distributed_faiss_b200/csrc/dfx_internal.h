@@ -56,6 +56,8 @@ struct dfx_index {
     bool tc_ready = false;
     bool tc_enabled = true;
     int rerank_variant = 1;  // 2 = rerank2_kernel (warp per query; dfx_set_param "rerank_variant")
+    bool flat_tc = false;       // FLAT: search through the tensor-core screening (dfx_tc_flat_candidates)
+    int64_t tc_flat_rows = -1;  // rows covered by the bf16 planes of a FLAT index (-1: none)
 
     // scan-kernel profiling (dfx_profile_enable)
     bool prof_on = false;
@@ -166,6 +168,7 @@ bool dfx_tc_supported(int d);
 void dfx_tc_prepare_centroids(dfx_index* idx, cudaStream_t st);
 void dfx_tc_coarse_search(dfx_index* idx, const float* d_x, int64_t nq, int nprobe, int32_t* keys,
                           cudaStream_t st);
+int dfx_tc_flat_candidates(dfx_index* idx, const float* d_x, int64_t nq, int k, cudaStream_t st);
 void dfx_tc_assign(dfx_index* idx, int d, const float* d_cent, const float* d_cnorm, int64_t nlist, int metric,
                    int64_t n, const float* d_x, int32_t* d_assign, cudaStream_t st);
 

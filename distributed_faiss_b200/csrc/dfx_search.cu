@@ -498,6 +498,29 @@ void dfx_search_impl(dfx_index* idx, int64_t nq, const float* d_x, int64_t k64, 
             dfx_launch_select<128>(ldr, wr, nq, 0, k, st);
             return;
         }
+        float* qnorm_tc = nullptr;
+        if (idx->flat_tc && idx->tc_enabled) {  // experimental: screening on tensor cores + exact re-rank
+            const int64_t ng = dfx_ceil_div(N, 128) * 4;
+            const int64_t QT = std::max<int64_t>(128, ((64ll << 20) / (ng * 4)) / 128 * 128);
+            bool handled = true;
+            for (int64_t q0 = 0; q0 < nq && handled; q0 += QT) {
+                const int64_t qc = std::min(QT, nq - q0);
+                const int ncand = dfx_tc_flat_candidates(idx, d_x + q0 * d, qc, k, st);
+                if (ncand == 0) {
+                    handled = false;  // shape not covered (only possible on the first chunk)
+                    break;
+                }
+                if (metric == DFX_METRIC_L2 && !qnorm_tc) {
+                    idx->w_dis0.reserve((size_t)nq * 4);
+                    qnorm_tc = idx->w_dis0.as<float>();
+                    dfx_launch_row_norms(d_x, nq, d, qnorm_tc, st);
+                }
+                CompLoader ldr{idx->tc_cand.as<uint64_t>(), ncand};
+                ResultWriter wr{d_D + q0 * k, d_I + q0 * k, k, metric, 0.f, qnorm_tc ? qnorm_tc + q0 : nullptr};
+                dfx_launch_select<128>(ldr, wr, qc, ncand, k, st);
+            }
+            if (handled) return;
+        }
         const int64_t NT = 32768;
         const int64_t ntiles = dfx_ceil_div(N, NT);
         int64_t QC = (32ll << 20) / NT;  // 1024 queries per chunk (128 MB of values)

@@ -918,6 +918,60 @@ void dfx_tc_coarse_search(dfx_index* idx, const float* d_x, int64_t nq, int npro
     }
 }
 
+// EXPERIMENTAL (dfx_set_param "flat_tensor_cores" = 1, off by default): flat search (reference
+// index.py:94 IndexFlatIP, and IndexFlatL2 of the C-ABI) through the same machinery, with the
+// database rows in place of the centroids and k in place of nprobe.  Screening on tensor cores
+// over bf16 planes of the rows (built lazily, rebuilt after an add), the k + 8 groups with the
+// smallest minima, exact canonical values of the columns the screening cannot rule out
+// (rerank_kernel<0>) -- the values gemm_values_kernel would have produced for them, bit for bit.
+// Leaves nq x ncand composites in idx->tc_cand; the caller selects and writes (D, I).
+// Returns ncand, or 0 when this shape is not handled (caller falls back to the FFMA GEMM).
+int dfx_tc_flat_candidates(dfx_index* idx, const float* d_x, int64_t nq, int k, cudaStream_t st) {
+    const int d = idx->cfg.d;
+    const int64_t N = idx->n_sorted;
+    if (!dfx_tc_supported(d) || N < 1024 || k > 100) return 0;
+    const int metric = idx->cfg.metric;
+    const int64_t nl_pad = dfx_ceil_div(N, tc::TILE) * tc::TILE;
+    const int ng = (int)(nl_pad / 32);
+    if (idx->tc_flat_rows != N) {  // (re)build the planes and the norm bound
+        idx->tc_cent.reserve((size_t)2 * nl_pad * d * 2);
+        DFX_LAUNCH(split_bf16_kernel, (unsigned)dfx_ceil_div(nl_pad * d, 256), 256, 0, st, idx->payload.as<float>(), N,
+                   nl_pad, d, idx->tc_cent.as<__nv_bfloat16>());
+        const float* norms = idx->xnorm.as<float>();
+        if (metric != DFX_METRIC_L2) {  // inner product keeps no row norms: the tolerance needs their maximum
+            idx->cnorm.reserve((size_t)N * 4);
+            dfx_launch_row_norms(idx->payload.as<float>(), N, d, idx->cnorm.as<float>(), st);
+            norms = idx->cnorm.as<float>();
+        }
+        idx->tc_cmax2 = max_norm2(idx, norms, N, st);
+        idx->tc_flat_rows = N;
+    }
+    int G = k + 8;
+    if (G > ng) G = ng;
+    const int ncand = G * 32;
+    idx->tc_gmin.reserve((size_t)nq * ng * 4);
+    idx->tc_gmin2.reserve((size_t)nq * ng * 4);
+    idx->tc_gargc.reserve((size_t)nq * ng);
+    idx->tc_groups.reserve((size_t)nq * G * 4);
+    idx->tc_cand.reserve((size_t)nq * ncand * 8);
+    tc_screen(idx, d, d_x, nq, idx->tc_cent.p, idx->xnorm.as<float>(), N, metric, idx->tc_gmin.as<float>(),
+              idx->tc_gmin2.as<float>(), idx->tc_gargc.as<uint8_t>(), st);
+    if (G <= 32 && ng >= 32) {
+        auto tk = topg_collect_kernel<256>;
+        DFX_LAUNCH(tk, (unsigned)dfx_ceil_div(nq, 8), 256, 0, st, idx->tc_gmin.as<float>(), nq, ng, G,
+                   idx->tc_groups.as<int32_t>());
+    } else {
+        dfx_launch_select_cols(idx->tc_gmin.as<float>(), nq, ng, ng, G, 0, idx->tc_groups.as<int32_t>(), nullptr,
+                               nullptr, 0, st);
+    }
+    auto kern = rerank_kernel<0>;
+    DFX_LAUNCH(kern, (unsigned)nq, 128, (size_t)d * 4, st, d_x, d, idx->payload.as<float>(), idx->xnorm.as<float>(), N,
+               metric, idx->tc_groups.as<int32_t>(), G, k, idx->tc_gmin.as<float>(), idx->tc_gmin2.as<float>(),
+               idx->tc_gargc.as<uint8_t>(), ng, idx->tc_cmax2, idx->tc_cand.as<uint64_t>(), (int32_t*)nullptr,
+               (const int32_t*)nullptr, (const int32_t*)nullptr, nq, (int32_t*)nullptr);
+    return ncand;
+}
+
 // nearest centroid per row (build path): screening, then the answer straight from the screening
 // summary when it is unambiguous, exact canonical evaluation for the (rare) ambiguous rows
 void dfx_tc_assign(dfx_index* idx, int d, const float* d_cent, const float* d_cnorm, int64_t nlist, int metric,

@@ -8,7 +8,7 @@
 set -u
 mkdir -p gpurun_out
 echo "== parity of the experimental variants (scan 2/3, prep 2, rerank 2) against the oracle"
-DFX_EXPERIMENTAL=1 timeout 600 python -m pytest tests -m gpu -q -x -k "scan_variant_2 or interleaved or ivf_matches or tensor_core_coarse" 2>&1 | tail -15 | tee gpurun_out/r2_v3_parity.log
+DFX_EXPERIMENTAL=1 timeout 600 python -m pytest tests -m gpu -q -x -k "scan_variant_2 or interleaved or ivf_matches or tensor_core_coarse or flat_tensor_core" 2>&1 | tail -15 | tee gpurun_out/r2_v3_parity.log
 if ! grep -q " passed" gpurun_out/r2_v3_parity.log || grep -q "failed" gpurun_out/r2_v3_parity.log; then
     echo "the experimental variants are NOT green: stop here, read gpurun_out/r2_v3_parity.log"
     exit 1
@@ -27,6 +27,9 @@ DFX_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_gpu_api.py -m gpu -q 
 timeout 600 python bench.py --nvec 100000000 --steps 20 --warmup 3 --sweep --no-cpu > gpurun_out/r2_bench_sweep_eager.json 2> gpurun_out/r2_bench_sweep_eager.err
 DFX_GRAPHS=1 timeout 600 python bench.py --nvec 100000000 --steps 20 --warmup 3 --sweep --no-cpu > gpurun_out/r2_bench_sweep_graphs.json 2> gpurun_out/r2_bench_sweep_graphs.err
 grep -o '"qps_by_batch": {[^}]*}' gpurun_out/r2_bench_sweep_eager.json gpurun_out/r2_bench_sweep_graphs.json
+echo "== the other configurations (flat 100k x 1k with and without the tensor-core path)"
+timeout 600 python scripts/bench_other_configs.py > gpurun_out/r2_other_configs.log 2>&1; tail -5 gpurun_out/r2_other_configs.log
+DFX_FLAT_TC=1 timeout 600 python scripts/bench_other_configs.py > gpurun_out/r2_other_configs_flat_tc.log 2>&1; tail -5 gpurun_out/r2_other_configs_flat_tc.log
 echo "== ncu: one full capture of the new scan kernel (bench.py opens the profiler window around the timed region)"
 DFX_SCAN_VARIANT=2 timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:scan_pq_il2 -c 2 \
     -o gpurun_out/r2_scan_pq_il2 python bench.py --steps 1 --warmup 1 > gpurun_out/r2_ncu.log 2>&1

@@ -478,3 +478,32 @@ def test_scan_variant_2_matches_oracle():
         g2.set_param("scan_variant", variant)
         for nq in (1, 13, 37):
             _assert_same(*g2.search(xq[:nq], 10), *o.search(xq[:nq], 10), f"prep 2, scan {variant}, nq={nq}")
+
+
+@pytest.mark.skipif(__import__("os").environ.get("DFX_EXPERIMENTAL") != "1",
+                    reason="flat search through the tensor-core screening has not been validated on hardware yet")
+@pytest.mark.parametrize("metric", [IP, L2])
+def test_flat_tensor_core_path_matches_oracle(metric):
+    """flat_tensor_cores=1: screening on tensor cores + exact canonical re-rank returns the bits of
+    the plain GEMM path and of the oracle (ties, k up to 100, rows added after the first search)"""
+    from oracle import oracle as O
+
+    E = _engine()
+    rs = np.random.RandomState(31)
+    d, n = 128, _sz(100_000, 5_000)
+    xb = clustered(rs, n, d, ncl=200)
+    xb[-300:] = xb[:300]                              # exact duplicates: ties decided by the id
+    xq = np.concatenate([xb[:20], clustered(rs, 17, d, ncl=200)])
+    g = E.GpuIndex(E.KIND_FLAT, d, metric)
+    o = O.make_index("flat", d, metric=metric)
+    g.add(xb[: n // 2]); o.add(xb[: n // 2])
+    for k in (1, 10, 33, 100):
+        Do, Io = o.search(xq, k)
+        g.set_param("flat_tensor_cores", 1)
+        _assert_same(*g.search(xq, k), Do, Io, f"flat TC k={k}")
+        g.set_param("flat_tensor_cores", 0)
+        _assert_same(*g.search(xq, k), Do, Io, f"flat GEMM k={k}")
+    g.add(xb[n // 2:]); o.add(xb[n // 2:])            # the bf16 planes must follow
+    g.set_param("flat_tensor_cores", 1)
+    _assert_same(*g.search(xq, 10), *o.search(xq, 10), "flat TC after add")
+    _assert_same(*g.search(xq[:1], 5), *o.search(xq[:1], 5), "flat TC nq=1")
