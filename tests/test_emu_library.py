@@ -38,6 +38,8 @@ SUBSET = [
     # coarse quantizer through the tensor-core path: screening restated in C++ (dfx_tc.cu, DFX_EMU),
     # group selection + exact re-rank + drivers are the product code
     "tests/test_gpu_parity.py::test_tensor_core_coarse_quantizer_matches_oracle[ivf_flat-1-64-0]",
+    "tests/test_gpu_parity.py::test_flat_tensor_core_path_matches_oracle[0]",    # flat_tensor_cores=1
+    "tests/test_gpu_parity.py::test_flat_tensor_core_path_matches_oracle[1]",
 ]
 
 
