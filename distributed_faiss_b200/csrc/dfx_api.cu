@@ -85,6 +85,8 @@ int dfx_create(const dfx_cfg* cfg, dfx_index** out) {
     }
     if (const char* e = getenv("DFX_RERANK_VARIANT"))
         if (atoi(e) == 2) idx->rerank_variant = 2;
+    if (const char* e = getenv("DFX_ROWS_INFLIGHT"))
+        if (atoi(e) == 8) idx->rows_inflight = 8;
     if (const char* e = getenv("DFX_FLAT_TC"))
         if (atoi(e) == 1) idx->flat_tc = true;
     DeviceGuard g(cfg->device);
@@ -125,6 +127,10 @@ int dfx_set_param(dfx_index* idx, const char* name, double value) {
         else if (idx->trained && idx->n_pending == 0 && idx->n_sorted > 0) dfx_pq_rm_to_il(idx, idx->stream);
     }
     else if (n == "flat_tensor_cores") idx->flat_tc = value != 0;
+    else if (n == "rows_inflight") {
+        DFX_REQUIRE(value == 4 || value == 8, "rows_inflight must be 4 or 8");
+        idx->rows_inflight = (int)value;
+    }
     else if (n == "rerank_variant") {
         DFX_REQUIRE(value == 1 || value == 2, "rerank_variant must be 1 or 2");
         idx->rerank_variant = (int)value;

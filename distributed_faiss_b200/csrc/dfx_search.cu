@@ -283,7 +283,10 @@ scan_pq_kernel(const float* __restrict__ lut, const float* __restrict__ dis0,
 //   MODE 1: fp32 rows, value = ||q-x||^2   (IVF-Flat, L2)
 //   MODE 2: fp16 residual codes, value = ||(q-c) - half2float(code)||^2   (IVF-SQ fp16)
 // =====================================================================================
-template <int MODE>
+// U = vectors in flight per warp: 4 (default), 8 = EXPERIMENTAL (dfx_set_param "rows_inflight"):
+// the kernel is bound by memory-level parallelism, not by instructions -- C2 (512 B per vector)
+// reaches 0.46 of the HBM peak and C4 (1536 B per vector) 0.68 with the same code.
+template <int MODE, int U = 4>
 __global__ void __launch_bounds__(128)
 scan_rows_kernel(const float* __restrict__ Q, int d, const float* __restrict__ cent,
                  const int32_t* __restrict__ keys, int nprobe, int G, int ngroups,
@@ -307,7 +310,6 @@ scan_rows_kernel(const float* __restrict__ Q, int d, const float* __restrict__ c
     wt.init(s_buf + (size_t)warp * cap, cap, k);
     __syncthreads();
 
-    constexpr int U = 4;  // vectors in flight per warp
     const int p_end = min(nprobe, (g + 1) * G);
     for (int p = g * G; p < p_end; p++) {
         const int l = keys[q * nprobe + p];
@@ -657,7 +659,7 @@ void dfx_search_impl(dfx_index* idx, int64_t nq, const float* d_x, int64_t k64, 
             const size_t smem = (((size_t)dq * 4 + 15) / 16) * 16 + (size_t)4 * cap * 8;
 #define DFX_SCAN_ROWS(MODE)                                                                      \
     do {                                                                                         \
-        auto kern = scan_rows_kernel<MODE>;                                                      \
+        auto kern = (idx->rows_inflight == 8) ? scan_rows_kernel<MODE, 8> : scan_rows_kernel<MODE, 4>; \
         DFX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,         \
                                       (int)smem));                                               \
         DFX_LAUNCH(kern, (unsigned)(qc * ngroups), 128, smem, st, xq, d, idx->centroids.as<float>(), \

@@ -27,9 +27,9 @@ DFX_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_gpu_api.py -m gpu -q 
 timeout 600 python bench.py --nvec 100000000 --steps 20 --warmup 3 --sweep --no-cpu > gpurun_out/r2_bench_sweep_eager.json 2> gpurun_out/r2_bench_sweep_eager.err
 DFX_GRAPHS=1 timeout 600 python bench.py --nvec 100000000 --steps 20 --warmup 3 --sweep --no-cpu > gpurun_out/r2_bench_sweep_graphs.json 2> gpurun_out/r2_bench_sweep_graphs.err
 grep -o '"qps_by_batch": {[^}]*}' gpurun_out/r2_bench_sweep_eager.json gpurun_out/r2_bench_sweep_graphs.json
-echo "== the other configurations (flat 100k x 1k with and without the tensor-core path)"
+echo "== the other configurations: default, then flat through the tensor-core path + 8 vectors in flight in the row scans"
 timeout 600 python scripts/bench_other_configs.py > gpurun_out/r2_other_configs.log 2>&1; tail -5 gpurun_out/r2_other_configs.log
-DFX_FLAT_TC=1 timeout 600 python scripts/bench_other_configs.py > gpurun_out/r2_other_configs_flat_tc.log 2>&1; tail -5 gpurun_out/r2_other_configs_flat_tc.log
+DFX_FLAT_TC=1 DFX_ROWS_INFLIGHT=8 timeout 600 python scripts/bench_other_configs.py > gpurun_out/r2_other_configs_flat_tc.log 2>&1; tail -5 gpurun_out/r2_other_configs_flat_tc.log
 echo "== ncu: one full capture of the new scan kernel (bench.py opens the profiler window around the timed region)"
 DFX_SCAN_VARIANT=2 timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:scan_pq_il2 -c 2 \
     -o gpurun_out/r2_scan_pq_il2 python bench.py --steps 1 --warmup 1 > gpurun_out/r2_ncu.log 2>&1
