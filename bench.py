@@ -451,12 +451,15 @@ def main():
         # batches, compare the ids of one batch with the default kernels' (they must be identical)
         ref_D, ref_I = group.search(batches[0], K)
         ref_I = ref_I.clone()
-        for label, sv, pv, rv in (("scan2", 2, 1, 1), ("scan2+prep2", 2, 2, 1), ("scan2+prep2+rerank2", 2, 2, 2),
+        for sh in shards:
+            sh.set_param("scan_ring", 0)
+        for label, sv, pv, rv in (("scan2", 2, 1, 1), ("scan2+ring", 2, 1, 1), ("scan2+prep2", 2, 2, 1), ("scan2+prep2+rerank2", 2, 2, 2),
                                   ("scan3", 3, 1, 1), ("rerank2", 1, 1, 2), ("default", 1, 1, 1)):
             for sh in shards:
                 sh.set_param("scan_variant", sv)
                 sh.set_param("prep_variant", pv)
                 sh.set_param("rerank_variant", rv)
+                sh.set_param("scan_ring", 1 if label.endswith("+ring") else 0)
             _, I_v = group.search(batches[0], K)
             same = bool(torch.equal(I_v, ref_I))
             for sh in shards:

@@ -85,6 +85,8 @@ int dfx_create(const dfx_cfg* cfg, dfx_index** out) {
     }
     if (const char* e = getenv("DFX_RERANK_VARIANT"))
         if (atoi(e) == 2) idx->rerank_variant = 2;
+    if (const char* e = getenv("DFX_IL2_RING"))
+        if (atoi(e) == 1) idx->il2_ring = true;
     if (const char* e = getenv("DFX_ROWS_INFLIGHT"))
         if (atoi(e) == 8) idx->rows_inflight = 8;
     if (const char* e = getenv("DFX_FLAT_TC"))
@@ -126,6 +128,7 @@ int dfx_set_param(dfx_index* idx, const char* name, double value) {
         if (!idx->il_enabled) dfx_pq_il_to_rm(idx, idx->stream);
         else if (idx->trained && idx->n_pending == 0 && idx->n_sorted > 0) dfx_pq_rm_to_il(idx, idx->stream);
     }
+    else if (n == "scan_ring") idx->il2_ring = value != 0;
     else if (n == "flat_tensor_cores") idx->flat_tc = value != 0;
     else if (n == "rows_inflight") {
         DFX_REQUIRE(value == 4 || value == 8, "rows_inflight must be 4 or 8");

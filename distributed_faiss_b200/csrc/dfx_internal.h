@@ -56,6 +56,7 @@ struct dfx_index {
     bool tc_ready = false;
     bool tc_enabled = true;
     int rerank_variant = 1;  // 2 = rerank2_kernel (warp per query; dfx_set_param "rerank_variant")
+    bool il2_ring = false;      // scan 2: feed the code blocks through shared-memory rings (dfx_set_param "scan_ring")
     int rows_inflight = 4;      // vectors in flight per warp of scan_rows_kernel (8: experimental)
     bool flat_tc = false;       // FLAT: search through the tensor-core screening (dfx_tc_flat_candidates)
     int64_t tc_flat_rows = -1;  // rows covered by the bf16 planes of a FLAT index (-1: none)

@@ -3,12 +3,13 @@
 #include "dfx_scan_il2_dev.cuh"
 #include <cstdlib>
 
-template <bool REG, int THREADS>
+template <bool REG, int THREADS, bool RING = false>
 static void launch_il2(dfx_index* idx, int64_t qc, const int32_t* keys, int nprobe, int G, int ngroups, int k, int cap,
                        uint64_t* part, cudaStream_t st) {
     constexpr int NW = THREADS / 32;
-    const size_t smem = (size_t)IL2_LUT_BYTES + (REG ? (size_t)NW * IL2_QCAP * 8 : (size_t)NW * cap * 8);
-    auto kern = scan_pq_il2_kernel<REG, THREADS>;
+    const size_t topk = REG ? (size_t)NW * IL2_QCAP * 8 : (size_t)NW * cap * 8;
+    const size_t smem = (size_t)IL2_LUT_BYTES + (RING ? (topk + 15) / 16 * 16 + (size_t)NW * IL2_RING * IL2_SLOT_BYTES : topk);
+    auto kern = scan_pq_il2_kernel<REG, THREADS, RING>;
     DFX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     DFX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     DFX_LAUNCH(kern, (unsigned)(qc * ngroups), THREADS, smem, st, idx->w_lut.as<float>(), idx->w_dis0.as<float>(), keys,
@@ -24,6 +25,10 @@ void dfx_launch_scan_pq_il2(dfx_index* idx, int64_t qc, const int32_t* keys, int
         return (e && atoi(e) == 384) ? 384 : 256;
     }();
     const bool reg = k <= 32;
+    if (idx->il2_ring && reg) {  // experimental: code blocks through per-warp cp.async.bulk rings
+        launch_il2<true, 256, true>(idx, qc, keys, nprobe, G, ngroups, k, cap, part, st);
+        return;
+    }
     // (the shared-memory top-k path sorts NW * cap entries with a bitonic network: NW must be a
     // power of two, so 12-warp CTAs are only used with the register top-k)
     if (threads == 384 && reg) {

@@ -86,8 +86,16 @@ __device__ __noinline__ Il2Flushed il2_flush(uint64_t kept, uint64_t* queue, int
 // lutW: [nq][256][64] (wide transposed table, pq_prep_kernel mode 2)
 // REG: k <= 32, register-resident top-k;  !REG: WarpTopK buffers in shared memory (any k)
 // THREADS: 256 (3 CTAs/SM) or 384 (2 CTAs/SM): 24 warps/SM either way, 3 vs 2 tables per SM
-template <bool REG, int THREADS = IL2_THREADS>
-__global__ void __launch_bounds__(THREADS, THREADS == 256 ? 3 : 2)
+// RING (EXPERIMENTAL, dfx_set_param "scan_ring" = 1): the code blocks do not travel through
+// registers but through a per-warp ring of IL2_RING shared-memory slots filled by cp.async.bulk
+// (TMA engine, one mbarrier per slot): the global->SM traffic leaves the LSU pipe entirely and
+// IL2_RING blocks per warp are in flight instead of two (bytes in flight per SM are what bounds
+// a latency-limited stream).  Costs 2 x 16-byte shared loads per lane and block, and shared memory:
+// 2 CTAs/SM of 8 warps.
+constexpr int IL2_RING = 4;             // slots per warp
+constexpr int IL2_SLOT_BYTES = 1024 + 128;  // codes + t-values of one block
+template <bool REG, int THREADS = IL2_THREADS, bool RING = false>
+__global__ void __launch_bounds__(THREADS, (RING || THREADS != 256) ? 2 : 3)
 scan_pq_il2_kernel(const float* __restrict__ lutW, const float* __restrict__ dis0, const int32_t* __restrict__ keys,
                    int nprobe, int G, int ngroups, const int64_t* __restrict__ blk_off,
                    const uint4* __restrict__ il_codes, const float* __restrict__ il_tvals,
@@ -95,7 +103,9 @@ scan_pq_il2_kernel(const float* __restrict__ lutW, const float* __restrict__ dis
     DFX_DYN_SMEM(unsigned char, smem_raw, 128);
     float* s_lut = reinterpret_cast<float*>(smem_raw);                      // [256][64]
     uint64_t* s_buf = reinterpret_cast<uint64_t*>(smem_raw + IL2_LUT_BYTES);  // queues / WarpTopK buffers
+    // RING: [LUT | queues or WarpTopK buffers | ring slots (16-byte aligned) | slot barriers]
     __shared__ __align__(8) uint64_t s_lut_bar;
+    __shared__ __align__(8) uint64_t s_slot_bar[RING ? (THREADS / 32) * IL2_RING : 1];
     __shared__ unsigned int s_cta_key;  // CTA-wide admission bound (order-preserving key)
     __shared__ int s_lb[IL2_MAXG], s_le[IL2_MAXG];  // first / end block of each probed list
     __shared__ float s_ld0[IL2_MAXG];               // |q - c|^2 of each probed list
@@ -113,6 +123,9 @@ scan_pq_il2_kernel(const float* __restrict__ lutW, const float* __restrict__ dis
     if (tid == 0) {
         s_cta_key = 0xff800000u;  // key of +inf: no bound yet
         dfx_bulk_init(&s_lut_bar);
+        if (RING)
+            for (int i = 0; i < (THREADS / 32) * IL2_RING; i++) dfx_bulk_init(&s_slot_bar[i]);
+        dfx_bulk_init_fence();
     }
     if (tid < np) {
         const int l = keys[q * nprobe + g * G + tid];
@@ -231,6 +244,54 @@ scan_pq_il2_kernel(const float* __restrict__ lutW, const float* __restrict__ dis
         }                                                                    \
     } while (0)
 
+    if (RING) {
+        // ---- ring-fed stream: slot s of this warp holds block (codes 1024 B | t 128 B)
+        const size_t topk_bytes = REG ? (size_t)IL2_NW * IL2_QCAP * 8 : (size_t)IL2_NW * cap * 8;
+        unsigned char* ring = smem_raw + IL2_LUT_BYTES + ((topk_bytes + 15) / 16) * 16 +
+                              (size_t)warp * IL2_RING * IL2_SLOT_BYTES;
+        uint64_t* bars = s_slot_bar + warp * IL2_RING;
+        const uint32_t ring_addr = dfx_smem_addr(ring);
+        int spos[IL2_RING];
+        float sd0[IL2_RING];
+        auto refill = [&](int s_) {  // warp-uniform; lane 0 issues the two copies of the next block
+            if (next_block()) {
+                spos[s_] = cur_b;
+                sd0[s_] = cur_d0;
+                if (lane == 0) {
+                    dfx_bulk_expect(&bars[s_], (uint32_t)IL2_SLOT_BYTES);
+                    dfx_bulk_copy(ring + (size_t)s_ * IL2_SLOT_BYTES, il_codes + (int64_t)cur_b * 64, 1024u, &bars[s_]);
+                    dfx_bulk_copy(ring + (size_t)s_ * IL2_SLOT_BYTES + 1024, il_tvals + (int64_t)cur_b * 32, 128u,
+                                  &bars[s_]);
+                }
+            } else {
+                spos[s_] = -1;
+            }
+        };
+#pragma unroll
+        for (int s_ = 0; s_ < IL2_RING; s_++) refill(s_);
+        uint32_t parity = 0;
+        bool more = true;
+        while (more) {
+#pragma unroll
+            for (int s_ = 0; s_ < IL2_RING; s_++) {
+                if (spos[s_] < 0) {
+                    more = false;
+                    break;
+                }
+                dfx_bulk_wait_parity(&bars[s_], parity);
+                const uint32_t slot = ring_addr + (uint32_t)(s_ * IL2_SLOT_BYTES);
+                const uint4 ca = dfx_lds_v4(slot + (uint32_t)lane * 16u);
+                const uint4 cb = dfx_lds_v4(slot + 512u + (uint32_t)lane * 16u);
+                const float tv = dfx_lds_f32(slot + 1024u + (uint32_t)lane * 4u);
+                const int pos = spos[s_];
+                const float d0 = sd0[s_];
+                __syncwarp();  // every lane has read the slot: it may be refilled
+                refill(s_);
+                process(ca, cb, tv, d0, pos);
+            }
+            parity ^= 1u;
+        }
+    } else {
     uint4 a0 = {}, b0 = {}, a1 = {}, b1 = {}, a2 = {}, b2 = {};
     float t0 = 0.f, t1 = 0.f, t2 = 0.f, e0 = 0.f, e1 = 0.f, e2 = 0.f;
     int p0, p1, p2;
@@ -247,6 +308,7 @@ scan_pq_il2_kernel(const float* __restrict__ lutW, const float* __restrict__ dis
         if (p2 < 0) break;
         process(a2, b2, t2, e2, p2);
     }
+    }  // !RING
 #undef IL2_FETCH
 
     uint64_t* out = part + ((int64_t)q * ngroups + g) * k;

@@ -102,7 +102,7 @@ scan_pq_il_body(const float* __restrict__ lutT, const float* __restrict__ dis0, 
     __shared__ unsigned int s_cta_key;  // CTA-wide admission bound (see WarpTopK::cta_key)
     if (tid == 0) {
         s_cta_key = 0xff800000u;  // order-preserving key of +inf: no bound yet
-        dfx_bulk_init(&s_lut_bar);
+        dfx_bulk_init_one(&s_lut_bar);
     }
     __syncthreads();
     if (tid == 0) dfx_bulk_issue(s_lut, lutT + q * 8192, 32768u, &s_lut_bar);

@@ -76,6 +76,8 @@ int dfx_add_dev(dfx_index *idx, int64_t n, const float *d_x, void *stream);
  * (dfx_scan_il2.cu; same results by construction, not yet validated on hardware), 3 the default
  * kernel on a block layout whose 128-bit loads are contiguous (same status);
  * "prep_variant" (1): 2 selects the experimental table-building kernel pq_prep2_kernel (same);
+ * "scan_ring" (0): 1 feeds scan variant 2 through per-warp cp.async.bulk rings in shared memory
+ * (experimental, same results);
  * "rows_inflight" (4): 8 keeps eight instead of four vectors per warp in flight in the
  * IVF-Flat / IVF-SQ list scan (experimental, same results);
  * "flat_tensor_cores" (0): 1 runs FLAT searches through the tensor-core screening + exact re-rank
