@@ -453,6 +453,9 @@ def test_scan_variant_2_matches_oracle():
         Do, Io = o.search(xq, k)
         g.set_param("scan_variant", 2)
         _assert_same(*g.search(xq, k), Do, Io, f"variant 2 nprobe={nprobe} k={k}")
+        g.set_param("scan_ring", 1)                   # same kernel fed through cp.async.bulk rings
+        _assert_same(*g.search(xq, k), Do, Io, f"variant 2 + ring nprobe={nprobe} k={k}")
+        g.set_param("scan_ring", 0)
         R2 = g.reconstruct_rows(ids)
         g.set_param("scan_variant", 3)                # the shipping kernel on coalesced halves
         _assert_same(*g.search(xq, k), Do, Io, f"variant 3 nprobe={nprobe} k={k}")
