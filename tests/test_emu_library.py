@@ -58,3 +58,19 @@ def test_gpu_parity_subset_on_the_emulated_library():
     tail = (run.stdout + run.stderr)[-3000:]
     assert run.returncode == 0, tail
     assert f"{len(SUBSET)} passed" in run.stdout, tail
+
+
+def test_fuzz_smoke_on_the_emulated_library():
+    """a few seconds of tests/emu/fuzz_against_oracle.py (random shapes, kinds, chunked adds, kernel
+    variants) -- the long runs are done by hand with the AddressSanitizer build"""
+    if shutil.which("g++") is None or platform.machine() != "x86_64":
+        pytest.skip("the emulator needs g++ on x86-64")
+    sys.path.insert(0, os.path.join(ROOT, "tests", "emu"))
+    try:
+        import build_emu_lib
+    finally:
+        sys.path.pop(0)
+    env = dict(os.environ, DFX_EMU_LIB=build_emu_lib.build())
+    run = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "emu", "fuzz_against_oracle.py"), "1000", "12"],
+                         cwd=ROOT, env=env, capture_output=True, text=True, timeout=600)
+    assert run.returncode == 0 and "0 failures" in run.stdout, (run.stdout + run.stderr)[-3000:]
