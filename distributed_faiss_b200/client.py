@@ -8,11 +8,15 @@ metric "dot" (client.py:291-292), shards that returned fewer than k hits padded 
 
 What is different underneath: the k-way merge that the reference runs on the CPU with
 faiss's `float_maxheap_array_t` (client.py:29-54) is the CUDA merge kernel K6 of libdfx
-(`engine.merge`, same semantics, pinned by the reference's golden vectors), and when the
-client is constructed over a `spmd.ShardGroup` the whole search -- query broadcast,
-per-shard search, result all-gather, merge -- stays on the GPUs and travels over
-NCCL/NVLink instead of pickled sockets.
+(same semantics, pinned by the reference's golden vectors), and when the client's process
+hosts a `spmd.SearchPlane` (one process per GPU under torchrun, the client in the process of
+plane rank 0) `search` / `search_with_filter` run as ONE collective: query broadcast,
+per-shard search, one all-gather of the packed (D, I) blocks and the merge all stay on the
+GPUs and travel over NCCL/NVLink; the pickled sockets (rpc.py) remain for the control plane
+and for the metadata OBJECTS of the winners.  Without a plane every call uses the sockets,
+exactly like the reference.
 """
+import collections.abc
 import itertools
 import logging
 import os
@@ -34,6 +38,55 @@ def _device_merge(Dall: np.ndarray, Iall: np.ndarray, negate: bool):
     from . import engine
 
     return engine.merge(Dall, Iall, negate=negate)
+
+
+class MetaRows(collections.abc.Sequence):
+    """`list[nq]` of `list[k]` of integer metadata, backed by the int64 matrix the device
+    returned (negative = no result -> None).  Behaves like the reference's list of lists
+    (indexing, iteration, len, == with lists); `tolist()` materialises it.  Building 40 960 Python
+    ints eagerly would cost more than the whole 8-GPU search of a 4096-query batch."""
+
+    __slots__ = ("_a",)
+
+    def __init__(self, a: np.ndarray):
+        self._a = a
+
+    def __len__(self):
+        return self._a.shape[0]
+
+    def _row(self, r):
+        row = r.tolist()
+        return [v if v >= 0 else None for v in row] if (r < 0).any() else row
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self._row(r) for r in self._a[i]]
+        return self._row(self._a[i])
+
+    def __iter__(self):
+        return (self._row(r) for r in self._a)
+
+    def __eq__(self, other):
+        if isinstance(other, MetaRows):
+            return np.array_equal(self._a, other._a)
+        try:
+            return self.tolist() == list(other)
+        except TypeError:
+            return NotImplemented
+
+    def __ne__(self, other):
+        r = self.__eq__(other)
+        return r if r is NotImplemented else not r
+
+    def __repr__(self):
+        return repr(self.tolist())
+
+    def tolist(self):
+        return [self._row(r) for r in self._a]
+
+    @property
+    def array(self) -> np.ndarray:
+        return self._a
 
 
 class ResultHeap:
@@ -72,6 +125,12 @@ class IndexClient:
         self.cur_server_ids = {}
         random.seed(time.time())
         self.cfg = IndexCfg.from_json(cfg_path) if cfg_path is not None else None
+        # NCCL data plane: attached when this process hosts a spmd.SearchPlane covering exactly
+        # the servers of the discovery file (rank-major); None = every call goes over the sockets
+        self.plane = None
+        self._meta_kind = {}      # index_id -> "int" | "object" (asked over the control plane)
+        self.lazy_metadata = True  # int fast path returns MetaRows instead of eager lists
+        self._attach_plane()
 
     # ------------------------------------------------------------ discovery / connections
     @staticmethod
@@ -102,8 +161,23 @@ class IndexClient:
     def _all(self, fn):
         return self.pool.map(fn, self.sub_indexes)
 
+    def _attach_plane(self, plane=None):
+        from . import spmd
+
+        plane = plane or spmd.current_plane()
+        if plane is None or plane.rank != 0 or plane.num_servers != self.num_indexes:
+            return False
+        if sorted(self.index_rank_to_id) != list(range(self.num_indexes)):
+            return False
+        self.plane = plane
+        return True
+
+    def detach_plane(self):
+        self.plane = None
+
     # ------------------------------------------------------------ control plane
     def create_index(self, index_id: str, cfg: Optional[IndexCfg] = None):
+        self._meta_kind.pop(index_id, None)
         if cfg is not None:
             self.cfg = cfg
         if self.cfg is None:
@@ -117,6 +191,7 @@ class IndexClient:
         self._all(lambda s: s.save_index(index_id))
 
     def load_index(self, index_id: str, cfg: Optional[IndexCfg] = None, force_reload: bool = True) -> bool:
+        self._meta_kind.pop(index_id, None)
         if force_reload:
             self._all(lambda s: s.drop_index(index_id))
         loaded = self._all(lambda s: s.load_index(index_id, cfg))
@@ -133,6 +208,7 @@ class IndexClient:
     def add_index_data(self, index_id: str, embeddings: np.ndarray, metadata: Optional[List[object]] = None,
                        train_async_if_triggered: bool = True) -> None:
         """First batch of an index goes to a random shard, then round-robin (client.py:186-192)."""
+        self._meta_kind.pop(index_id, None)
         if index_id not in self.cur_server_ids:
             self.cur_server_ids[index_id] = random.randint(0, self.num_indexes - 1)
         target = self.cur_server_ids[index_id]
@@ -177,6 +253,8 @@ class IndexClient:
     # ------------------------------------------------------------ the hot path
     def search(self, query, topk: int, index_id: str, return_embeddings: bool = False) -> Tuple[np.ndarray, List]:
         maximize_metric: bool = self.cfg.metric == "dot"
+        if self.plane is not None:
+            return self._search_plane(query, topk, index_id, return_embeddings, maximize_metric)
         results = self.pool.imap(lambda s: s.search(index_id, query, topk, return_embeddings), self.sub_indexes)
         return self._aggregate_results(results, topk, query.shape[0], maximize_metric, return_embeddings)
 
@@ -186,6 +264,8 @@ class IndexClient:
         (client.py:213-263).  Returns per-query lists (possibly shorter than top_k)."""
         if filter_pos < 0:
             return self.search(query, top_k, index_id)
+        if self.plane is not None:
+            return self._search_with_filter_plane(query, top_k, index_id, filter_pos, filter_value)
         scores, meta = self.search(query, 3 * top_k, index_id)
         out_scores, out_meta = [], []
         for row_scores, row_meta in zip(scores, meta):
@@ -193,6 +273,80 @@ class IndexClient:
                     if m and len(m) > filter_pos and m[filter_pos] != filter_value][:top_k]
             out_meta.append([m for _, m in kept])
             out_scores.append(np.array([s for s, _ in kept], dtype=np.float32).reshape(-1, 1))
+        return out_scores, out_meta
+
+    # ---- NCCL data plane (spmd.SearchPlane): same contracts, one collective instead of S RPCs
+    def _get_meta_kind(self, index_id: str) -> str:
+        kind = self._meta_kind.get(index_id)
+        if kind is None:
+            kinds = self._all(lambda s: s.get_meta_kind(index_id))
+            kind = "int" if all(k == "int" for k in kinds) else "object"
+            self._meta_kind[index_id] = kind
+        return kind
+
+    def _exchange_ids_to_meta(self, index_id: str, I: np.ndarray) -> List[List[object]]:
+        """exchange ids ((server rank << 40) | local id) -> metadata objects: shards hosted by this
+        process are read directly, the others over their control-plane socket"""
+        from . import spmd
+
+        flat = I.reshape(-1)
+        out = np.empty(flat.shape[0], dtype=object)  # None where I < 0
+        valid = flat >= 0
+        owner = np.where(valid, (flat >> spmd.LOCAL_BITS) & 0xFFFFF, -1)
+        local = flat & spmd.LOCAL_MASK
+        for sr in np.unique(owner[valid]).tolist():
+            sel = np.nonzero(owner == sr)[0]
+            srv = self.plane.owner_of(int(sr))
+            if srv is not None:
+                metas = srv.lookup_meta(index_id, local[sel])
+            else:
+                metas = self.sub_indexes[self.index_rank_to_id[int(sr)]].lookup_meta(index_id, local[sel])
+            tmp = np.empty(len(metas), dtype=object)
+            tmp[:] = metas
+            out[sel] = tmp
+        return out.reshape(I.shape).tolist()
+
+    def _search_plane(self, query, topk, index_id, return_embeddings, maximize_metric):
+        from . import spmd
+
+        for attempt in (0, 1):
+            int_meta = self._get_meta_kind(index_id) == "int"
+            try:
+                D, I, _cnt, embs, meta_int = self.plane.search(
+                    index_id, query, topk, maximize=maximize_metric, return_embeddings=return_embeddings,
+                    int_meta=int_meta)
+                break
+            except spmd.MetaKindChanged:
+                self._meta_kind.pop(index_id, None)
+                if attempt:
+                    raise
+            except spmd.PlaneError as e:
+                raise rpc.ServerException(str(e))
+        if int_meta:
+            # with embeddings I holds exchange ids (the owners decoded by them) and the integer
+            # metadata of the winners came back separately
+            ids = np.where(I < 0, -1, meta_int) if return_embeddings else I
+            meta = MetaRows(ids) if self.lazy_metadata else MetaRows(ids).tolist()
+        else:
+            meta = self._exchange_ids_to_meta(index_id, I)
+        if not return_embeddings:
+            return D, meta
+        # the reference returns list[nq][k] of per-winner vectors (client.py:299-307)
+        picked = [[embs[q, j] if I[q, j] >= 0 else None for j in range(I.shape[1])] for q in range(I.shape[0])]
+        return D, meta, picked
+
+    def _search_with_filter_plane(self, query, top_k, index_id, filter_pos, filter_value):
+        from . import spmd
+
+        try:
+            D, I, cnt, _e, _m = self.plane.search(index_id, query, 3 * top_k, maximize=self.cfg.metric == "dot",
+                                                  filter_pos=filter_pos, filter_value=filter_value, k_out=top_k)
+        except spmd.PlaneError as e:
+            raise rpc.ServerException(str(e))
+        meta = self._exchange_ids_to_meta(index_id, I)
+        cnt = cnt.tolist()
+        out_scores = [np.ascontiguousarray(D[q, :c], dtype=np.float32).reshape(-1, 1) for q, c in enumerate(cnt)]
+        out_meta = [meta[q][:c] for q, c in enumerate(cnt)]
         return out_scores, out_meta
 
     @staticmethod

@@ -266,6 +266,17 @@ int dfx_reconstruct(dfx_index* idx, int64_t n, const int64_t* ids, float* out) {
     DFX_API_END
 }
 
+int dfx_reconstruct_dev(dfx_index* idx, int64_t n, const int64_t* d_ids, int64_t shard_tag, float* d_out,
+                        void* stream) {
+    DFX_API_BEGIN
+    std::lock_guard<std::mutex> lk(idx->mu);
+    DeviceGuard g(idx->cfg.device);
+    idx->join_dev_if_other((cudaStream_t)stream);
+    dfx_reconstruct_impl(idx, n, d_ids, d_out, (cudaStream_t)stream, shard_tag);
+    idx->note_dev((cudaStream_t)stream);
+    DFX_API_END
+}
+
 int dfx_set_nprobe(dfx_index* idx, int64_t nprobe) {
     DFX_API_BEGIN
     DFX_REQUIRE(nprobe >= 1, "nprobe must be >= 1");
@@ -311,6 +322,26 @@ int dfx_merge(int64_t S, int64_t nq, int64_t k, const float* D, const int64_t* I
     dfx_merge_impl(S, nq, k, dD.as<float>(), dI.as<int64_t>(), negate, oD.as<float>(), oI.as<int64_t>(), 0);
     DFX_CUDA(cudaMemcpy(outD, oD.p, (size_t)nq * k * 4, cudaMemcpyDeviceToHost));
     DFX_CUDA(cudaMemcpy(outI, oI.p, (size_t)nq * k * 8, cudaMemcpyDeviceToHost));
+    DFX_API_END
+}
+int dfx_merge_packed_dev(int64_t R, int64_t S_loc, int64_t nq, int64_t k, const void* d_packed,
+                         int64_t rank_stride_bytes, int64_t off_I_bytes, int negate, float* d_outD,
+                         int64_t* d_outI, void* stream) {
+    DFX_API_BEGIN
+    dfx_merge_packed_impl(R, S_loc, nq, k, d_packed, rank_stride_bytes, off_I_bytes, negate, d_outD, d_outI,
+                          (cudaStream_t)stream);
+    DFX_API_END
+}
+int dfx_encode_ids_dev(int64_t n, const int64_t* d_ids, int64_t shard_tag, const int32_t* d_col,
+                       int32_t drop_code, int64_t* d_out, void* stream) {
+    DFX_API_BEGIN
+    dfx_encode_ids_impl(n, d_ids, shard_tag, d_col, drop_code, d_out, (cudaStream_t)stream);
+    DFX_API_END
+}
+int dfx_filter_compact_dev(int64_t nq, int64_t k_in, int64_t k_out, const float* d_D, const int64_t* d_I,
+                           float* d_outD, int64_t* d_outI, int32_t* d_count, void* stream) {
+    DFX_API_BEGIN
+    dfx_filter_compact_impl(nq, k_in, k_out, d_D, d_I, d_outD, d_outI, d_count, (cudaStream_t)stream);
     DFX_API_END
 }
 int dfx_map_ids_dev(int64_t n, const int64_t* d_ids, const int64_t* d_table, int64_t* d_out, void* stream) {

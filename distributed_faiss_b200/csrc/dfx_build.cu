@@ -535,9 +535,16 @@ __global__ void reconstruct_kernel(int kind, int d, int M, int ksub, int dsub, i
                                    const int32_t* __restrict__ inv, const void* __restrict__ rows,
                                    const int64_t* __restrict__ list_off, const float* __restrict__ cent,
                                    const float* __restrict__ codebooks, int il,
-                                   const int64_t* __restrict__ blk_off, float* __restrict__ out) {
+                                   const int64_t* __restrict__ blk_off, float* __restrict__ out,
+                                   int64_t tag) {
     const int64_t r = blockIdx.x;
-    const int64_t id = want[r];
+    int64_t id = want[r];
+    if (tag >= 0) {
+        // exchange ids ((shard tag << 40) | local id, see encode_ids_kernel): decode only the rows
+        // this shard owns and leave every other row of `out` untouched
+        if (id < 0 || ((id >> 40) & 0xfffff) != tag) return;
+        id &= (1ll << 40) - 1;
+    }
     if (id < 0 || id >= ntotal) {
         for (int k = threadIdx.x; k < d; k += blockDim.x) out[r * d + k] = __int_as_float(0x7fc00000);
         return;
@@ -572,7 +579,7 @@ __global__ void reconstruct_kernel(int kind, int d, int M, int ksub, int dsub, i
 }
 
 void dfx_reconstruct_impl(dfx_index* idx, int64_t n, const int64_t* d_ids, float* d_out,
-                          cudaStream_t st) {
+                          cudaStream_t st, int64_t tag) {
     if (n <= 0) return;
     if (idx->n_pending > 0) dfx_finalize_impl(idx, st);
     const int64_t nt = idx->n_sorted;
@@ -588,5 +595,5 @@ void dfx_reconstruct_impl(dfx_index* idx, int64_t n, const int64_t* d_ids, float
     DFX_LAUNCH(reconstruct_kernel, (unsigned)n, 128, 0, st, idx->cfg.kind, idx->cfg.d, idx->M, idx->ksub,
                idx->dsub, nt, idx->cfg.nlist, d_ids, idx->inv.as<int32_t>(),
                il ? (const void*)idx->il_codes.p : (const void*)idx->payload.p, idx->list_off.as<int64_t>(),
-               idx->centroids.as<float>(), idx->codebooks.as<float>(), il, idx->blk_off.as<int64_t>(), d_out);
+               idx->centroids.as<float>(), idx->codebooks.as<float>(), il, idx->blk_off.as<int64_t>(), d_out, tag);
 }

@@ -118,6 +118,13 @@ void dfx_search_impl(dfx_index* idx, int64_t nq, const float* d_x, int64_t k, fl
                      int64_t* d_I, cudaStream_t st);
 void dfx_merge_impl(int64_t S, int64_t nq, int64_t k, const float* d_D, const int64_t* d_I,
                     int negate, float* d_outD, int64_t* d_outI, cudaStream_t st);
+void dfx_merge_packed_impl(int64_t R, int64_t S_loc, int64_t nq, int64_t k, const void* d_packed,
+                           int64_t rank_stride, int64_t off_I, int negate, float* d_outD,
+                           int64_t* d_outI, cudaStream_t st);
+void dfx_encode_ids_impl(int64_t n, const int64_t* d_ids, int64_t tag, const int32_t* d_col,
+                         int32_t drop_code, int64_t* d_out, cudaStream_t st);
+void dfx_filter_compact_impl(int64_t nq, int64_t kin, int64_t kout, const float* d_D, const int64_t* d_I,
+                             float* d_outD, int64_t* d_outI, int32_t* d_count, cudaStream_t st);
 void dfx_map_ids_impl(int64_t n, const int64_t* d_ids, const int64_t* d_table, int64_t* d_out,
                       cudaStream_t st);
 void dfx_stats_impl(dfx_index* idx, int64_t* ndis, cudaStream_t st);
@@ -178,8 +185,10 @@ void dfx_tc_assign(dfx_index* idx, int d, const float* d_cent, const float* d_cn
 void dfx_train_impl(dfx_index* idx, int64_t n, const float* d_x, cudaStream_t st);
 void dfx_add_impl(dfx_index* idx, int64_t n, const float* d_x, cudaStream_t st);
 void dfx_finalize_impl(dfx_index* idx, cudaStream_t st);
+// tag < 0: d_ids are shard-local ids (unknown / -1 rows become NaN); tag >= 0: d_ids are exchange
+// ids and only the rows owned by shard `tag` are written
 void dfx_reconstruct_impl(dfx_index* idx, int64_t n, const int64_t* d_ids, float* d_out,
-                          cudaStream_t st);
+                          cudaStream_t st, int64_t tag = -1);
 // fused nearest-centroid (GEMM + argmin epilogue), no values matrix
 void dfx_launch_assign_fused(const float* X, int64_t n, const float* cent, const float* cnorm,
                              int64_t nlist, int d, int metric, unsigned long long* best,

@@ -438,6 +438,121 @@ void dfx_map_ids_impl(int64_t n, const int64_t* d_ids, const int64_t* d_table, i
     DFX_LAUNCH(map_ids_kernel, (unsigned)dfx_ceil_div(n, 256), 256, 0, st, n, d_ids, d_table, d_out);
 }
 
+// ---- packed exchange form: what ONE all-gather over the ranks delivers.  Rank r's block starts at
+// base + r * rank_stride and holds D f32[S_loc][nq][k] at offset 0 and I i64[S_loc][nq][k] at
+// off_I.  Shard s = r * S_loc + j (rank-major), same total order as dfx_merge_impl.
+struct MergePackedLoader {
+    const unsigned char* base;
+    int64_t rank_stride, nq;
+    int k, s_loc, negate;
+    __device__ __forceinline__ uint64_t operator()(int64_t row, int e) const {
+        int s = e / k, j = e - s * k;
+        int r = s / s_loc, sl = s - r * s_loc;
+        const float* D = reinterpret_cast<const float*>(base + (int64_t)r * rank_stride);
+        float v = D[((int64_t)sl * nq + row) * k + j];
+        if (negate) v = -v;
+        if (!(v < FLT_MAX)) return DFX_COMP_NONE;
+        return dfx_comp(v, (uint32_t)e);
+    }
+};
+struct MergePackedWriter {
+    const unsigned char* base;
+    int64_t rank_stride, off_I, nq;
+    int k, s_loc;
+    float* outD;
+    int64_t* outI;
+    __device__ __forceinline__ void operator()(int64_t row, int j, uint64_t c) const {
+        if (c == DFX_COMP_NONE) {
+            outD[row * k + j] = FLT_MAX;
+            outI[row * k + j] = -1;
+        } else {
+            uint32_t e = (uint32_t)c;
+            int s = e / k, jj = e - s * k;
+            int r = s / s_loc, sl = s - r * s_loc;
+            const int64_t* I = reinterpret_cast<const int64_t*>(base + (int64_t)r * rank_stride + off_I);
+            outD[row * k + j] = dfx_key2f((uint32_t)(c >> 32));
+            outI[row * k + j] = I[((int64_t)sl * nq + row) * k + jj];
+        }
+    }
+};
+void dfx_merge_packed_impl(int64_t R, int64_t S_loc, int64_t nq, int64_t k, const void* d_packed,
+                           int64_t rank_stride, int64_t off_I, int negate, float* d_outD,
+                           int64_t* d_outI, cudaStream_t st) {
+    DFX_REQUIRE(R >= 1 && S_loc >= 1 && k >= 1 && R * S_loc * k < (1ll << 31), "merge: bad R/S/k");
+    DFX_REQUIRE(rank_stride % 8 == 0 && off_I % 8 == 0 && off_I >= S_loc * nq * k * 4,
+                "merge: the packed blocks must be 8-byte aligned and I must follow D");
+    if (nq <= 0) return;
+    const unsigned char* b = reinterpret_cast<const unsigned char*>(d_packed);
+    MergePackedLoader ldr{b, rank_stride, nq, (int)k, (int)S_loc, negate};
+    MergePackedWriter wr{b, rank_stride, off_I, nq, (int)k, (int)S_loc, d_outD, d_outI};
+    dfx_launch_select<128>(ldr, wr, nq, (int)(R * S_loc * k), (int)k, st);
+}
+
+// shard-local ids -> exchange ids: (shard tag << 40) | local id, -1 stays -1.  With a metadata
+// column (int32 code per local id; -2 = the entry has no such metadata position) the entries the
+// reference's post-filter would drop (client.py:235-243: meta[filter_pos] == filter_value, or no
+// metadata / too short) get bit 62 set; the flag rides through all-gather + merge untouched.
+__global__ void encode_ids_kernel(int64_t n, const int64_t* __restrict__ ids, int64_t tag,
+                                  const int32_t* __restrict__ col, int32_t drop_code,
+                                  int64_t* __restrict__ out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int64_t v = ids[i];
+    if (v < 0) {
+        out[i] = -1;
+        return;
+    }
+    int64_t e = (tag << 40) | v;
+    if (col) {
+        int32_t c = col[v];
+        if (c == drop_code || c == -2) e |= (1ll << 62);
+    }
+    out[i] = e;
+}
+void dfx_encode_ids_impl(int64_t n, const int64_t* d_ids, int64_t tag, const int32_t* d_col,
+                         int32_t drop_code, int64_t* d_out, cudaStream_t st) {
+    DFX_REQUIRE(tag >= 0 && tag < (1ll << 20), "encode_ids: shard tag out of range");
+    if (n <= 0) return;
+    DFX_LAUNCH(encode_ids_kernel, (unsigned)dfx_ceil_div(n, 256), 256, 0, st, n, d_ids, tag, d_col, drop_code, d_out);
+}
+
+// post-filter of search_with_filter on device (client.py:229-250): per query walk the kin merged
+// slots in rank order, keep the entries that exist (I >= 0) and do not carry the drop flag, stop
+// at kout.  One warp per query; ballot + prefix popcount keeps the order.
+__global__ void filter_compact_kernel(int64_t nq, int kin, int kout, const float* __restrict__ D,
+                                      const int64_t* __restrict__ I, float* __restrict__ outD,
+                                      int64_t* __restrict__ outI, int32_t* __restrict__ outCount) {
+    const int64_t q = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (q >= nq) return;
+    int kept = 0;
+    for (int j0 = 0; j0 < kin && kept < kout; j0 += 32) {
+        int j = j0 + lane;
+        int64_t id = (j < kin) ? I[q * kin + j] : -1;
+        bool keep = id >= 0 && !(id & (1ll << 62));
+        unsigned m = __ballot_sync(0xffffffffu, keep);
+        int pos = kept + __popc(m & ((1u << lane) - 1u));
+        if (keep && pos < kout) {
+            outD[q * kout + pos] = D[q * kin + j];
+            outI[q * kout + pos] = id;
+        }
+        kept += __popc(m);
+    }
+    if (kept > kout) kept = kout;
+    for (int j = kept + lane; j < kout; j += 32) {
+        outD[q * kout + j] = FLT_MAX;
+        outI[q * kout + j] = -1;
+    }
+    if (lane == 0) outCount[q] = kept;
+}
+void dfx_filter_compact_impl(int64_t nq, int64_t kin, int64_t kout, const float* d_D, const int64_t* d_I,
+                             float* d_outD, int64_t* d_outI, int32_t* d_count, cudaStream_t st) {
+    DFX_REQUIRE(kin >= 1 && kout >= 1 && kin < (1 << 20), "filter: bad k");
+    if (nq <= 0) return;
+    DFX_LAUNCH(filter_compact_kernel, (unsigned)dfx_ceil_div(nq, 4), 128, 0, st, nq, (int)kin, (int)kout, d_D, d_I,
+               d_outD, d_outI, d_count);
+}
+
 // ndis of the last search = sum over (q,p) of len(list keys[q][p])
 __global__ void ndis_kernel(const int32_t* __restrict__ keys, int64_t n,
                             const int64_t* __restrict__ list_off, unsigned long long* out) {

@@ -32,7 +32,8 @@ EXPORTED_SYMBOLS = [
     "dfx_create", "dfx_destroy", "dfx_train", "dfx_add", "dfx_train_dev", "dfx_add_dev", "dfx_set_param",
     "dfx_reserve", "dfx_finalize", "dfx_search", "dfx_search_dev", "dfx_reconstruct", "dfx_set_nprobe",
     "dfx_get_nprobe", "dfx_ntotal", "dfx_nlist", "dfx_is_trained", "dfx_get_centroids", "dfx_merge",
-    "dfx_merge_dev", "dfx_map_ids_dev", "dfx_get_array", "dfx_set_array", "dfx_import_done",
+    "dfx_merge_dev", "dfx_merge_packed_dev", "dfx_encode_ids_dev", "dfx_filter_compact_dev",
+    "dfx_reconstruct_dev", "dfx_map_ids_dev", "dfx_get_array", "dfx_set_array", "dfx_import_done",
     "dfx_last_stats", "dfx_profile_enable", "dfx_profile_read", "dfx_launch_count", "dfx_synth_init", "dfx_synth_rows_dev", "dfx_free",
     "dfx_last_error", "dfx_version", "dfx_debug_il_byte",
 ]
@@ -213,6 +214,20 @@ class GpuIndex:
         _check(lib().dfx_reconstruct(self._h, C.c_int64(ids.shape[0]), _np_ptr(ids), _np_ptr(out)))
         return out
 
+    def reconstruct_dev(self, ids_t, out_t, shard_tag=-1):
+        """Decode on device.  shard_tag < 0: ids_t are shard-local ids; shard_tag >= 0: ids_t are
+        exchange ids (encode_ids_dev) and only the rows this shard owns are written into out_t."""
+        import torch
+
+        assert ids_t.is_cuda and ids_t.dtype == torch.int64 and ids_t.is_contiguous()
+        assert out_t.is_cuda and out_t.dtype == torch.float32 and out_t.is_contiguous()
+        n = ids_t.numel()
+        assert out_t.numel() == n * self.d
+        st = torch.cuda.current_stream(ids_t.device).cuda_stream
+        _check(lib().dfx_reconstruct_dev(self._h, C.c_int64(n), C.c_void_p(ids_t.data_ptr()),
+                                         C.c_int64(int(shard_tag)), C.c_void_p(out_t.data_ptr()), C.c_void_p(st)))
+        return out_t
+
     def search_and_reconstruct(self, x, k):
         D, I = self.search(x, k)
         R = self.reconstruct_rows(I).reshape(I.shape[0], I.shape[1], self.d)
@@ -320,6 +335,59 @@ def merge_dev(D_t, I_t, negate=False, outD=None, outI=None):
                                C.c_void_p(I_t.data_ptr()), C.c_int(1 if negate else 0),
                                C.c_void_p(outD.data_ptr()), C.c_void_p(outI.data_ptr()), C.c_void_p(st)))
     return outD, outI
+
+
+def merge_packed_dev(packed_t, R, S_loc, nq, k, rank_stride, off_I, negate=False, outD=None, outI=None):
+    """K6 over the buffer ONE all-gather delivers (layout: include/dfx.h dfx_merge_packed_dev)."""
+    import torch
+
+    assert packed_t.is_cuda and packed_t.is_contiguous() and packed_t.dtype == torch.uint8
+    assert packed_t.numel() >= R * rank_stride
+    if outD is None:
+        outD = torch.empty((nq, k), dtype=torch.float32, device=packed_t.device)
+    if outI is None:
+        outI = torch.empty((nq, k), dtype=torch.int64, device=packed_t.device)
+    st = torch.cuda.current_stream(packed_t.device).cuda_stream
+    _check(lib().dfx_merge_packed_dev(C.c_int64(R), C.c_int64(S_loc), C.c_int64(nq), C.c_int64(k),
+                                      C.c_void_p(packed_t.data_ptr()), C.c_int64(rank_stride), C.c_int64(off_I),
+                                      C.c_int(1 if negate else 0), C.c_void_p(outD.data_ptr()),
+                                      C.c_void_p(outI.data_ptr()), C.c_void_p(st)))
+    return outD, outI
+
+
+EXCHANGE_LOCAL_BITS = 40            # exchange id = (shard tag << 40) | shard-local id
+EXCHANGE_DROP_FLAG = 1 << 62        # set on entries search_with_filter's post-filter drops
+
+
+def encode_ids_dev(ids_t, shard_tag, out_t=None, col_t=None, drop_code=-1):
+    import torch
+
+    if out_t is None:
+        out_t = torch.empty_like(ids_t)
+    assert ids_t.dtype == torch.int64 and out_t.dtype == torch.int64
+    assert col_t is None or (col_t.dtype == torch.int32 and col_t.is_cuda)
+    st = torch.cuda.current_stream(ids_t.device).cuda_stream
+    _check(lib().dfx_encode_ids_dev(C.c_int64(ids_t.numel()), C.c_void_p(ids_t.data_ptr()), C.c_int64(int(shard_tag)),
+                                    C.c_void_p(col_t.data_ptr()) if col_t is not None else None,
+                                    C.c_int32(int(drop_code)), C.c_void_p(out_t.data_ptr()), C.c_void_p(st)))
+    return out_t
+
+
+def filter_compact_dev(D_t, I_t, k_out):
+    """search_with_filter's post-filter on device: (D, I) [nq, k_in] merged -> the first k_out kept
+    entries per query, padded with (FLT_MAX, -1), and the number kept per query."""
+    import torch
+
+    nq, k_in = D_t.shape
+    assert D_t.is_contiguous() and I_t.is_contiguous()
+    outD = torch.empty((nq, k_out), dtype=torch.float32, device=D_t.device)
+    outI = torch.empty((nq, k_out), dtype=torch.int64, device=D_t.device)
+    cnt = torch.empty((nq,), dtype=torch.int32, device=D_t.device)
+    st = torch.cuda.current_stream(D_t.device).cuda_stream
+    _check(lib().dfx_filter_compact_dev(C.c_int64(nq), C.c_int64(k_in), C.c_int64(k_out), C.c_void_p(D_t.data_ptr()),
+                                        C.c_void_p(I_t.data_ptr()), C.c_void_p(outD.data_ptr()),
+                                        C.c_void_p(outI.data_ptr()), C.c_void_p(cnt.data_ptr()), C.c_void_p(st)))
+    return outD, outI, cnt
 
 
 def map_ids_dev(ids_t, table_t, out_t=None):

@@ -40,25 +40,29 @@ INDEX_FILE = "index.dfx.npz"
 FAISS_INDEX_FILE = "index.faiss"
 
 
-def default_engine_factory(cfg: IndexCfg):
-    """cfg -> GPU engine object (the CUDA library is loaded here; fails loudly without it)."""
+def default_engine_factory(cfg: IndexCfg, device: Optional[int] = None):
+    """cfg -> GPU engine object (the CUDA library is loaded here; fails loudly without it).
+    `device`: the GPU ordinal of the owning IndexServer rank; None = the calling thread's current
+    device (only safe on the thread that was pinned, see Index._bind_device)."""
     from . import engine
 
     btype = cfg.index_builder_type
     if btype == "flat":
-        return engine.GpuIndex(engine.KIND_FLAT, cfg.dim, METRIC_INNER_PRODUCT)
+        return engine.GpuIndex(engine.KIND_FLAT, cfg.dim, METRIC_INNER_PRODUCT, device=device)
     if btype == "ivf_simple":
-        idx = engine.GpuIndex(engine.KIND_IVF_FLAT, cfg.dim, cfg.get_metric(), nlist=int(cfg.centroids))
+        idx = engine.GpuIndex(engine.KIND_IVF_FLAT, cfg.dim, cfg.get_metric(), nlist=int(cfg.centroids),
+                              device=device)
         idx.nprobe = cfg.nprobe
         return idx
     if btype == "knnlm":
         idx = engine.GpuIndex(engine.KIND_IVF_PQ, cfg.dim, cfg.get_metric(), nlist=int(cfg.centroids),
                               pq_m=int(cfg.extra.get("code_size", 64)),
-                              pq_nbits=int(cfg.extra.get("bits_per_vector", 8)))
+                              pq_nbits=int(cfg.extra.get("bits_per_vector", 8)), device=device)
         cfg.nprobe = idx.nprobe  # the reference copies the index default back into cfg (index.py:47)
         return idx
     if btype == "ivfsq":
-        idx = engine.GpuIndex(engine.KIND_IVF_SQ16, cfg.dim, cfg.get_metric(), nlist=int(cfg.centroids))
+        idx = engine.GpuIndex(engine.KIND_IVF_SQ16, cfg.dim, cfg.get_metric(), nlist=int(cfg.centroids),
+                              device=device)
         idx.nprobe = cfg.nprobe
         return idx
     if btype in ("hnswsq", "ivf_gpu") or cfg.faiss_factory:
@@ -68,18 +72,61 @@ def default_engine_factory(cfg: IndexCfg):
     raise RuntimeError("Either faiss_factory or valid index_builder_type should be specified to initialize index")
 
 
+class IntMetadata:
+    """`id_to_metadata` of a shard adopted from the device: local id -> integer, kept as an int64
+    tensor (1 B vectors worth of Python ints would not fit a host).  Read-only sequence."""
+
+    def __init__(self, table):
+        self.table = table
+        self._host = None
+
+    def __len__(self):
+        return int(self.table.shape[0])
+
+    def __getitem__(self, i):
+        return int(self.table[i])
+
+    def lookup(self, ids: np.ndarray):
+        import torch
+
+        ids = np.asarray(ids, dtype=np.int64)
+        t = torch.from_numpy(np.where(ids < 0, 0, ids).reshape(-1)).to(self.table.device)
+        vals = self.table[t].cpu().numpy().reshape(ids.shape)
+        out = vals.astype(object)
+        out[ids < 0] = None
+        return out.tolist()
+
+
 def get_index_files(index_storage_dir: str) -> Tuple[str, str, str, str]:
     return tuple(os.path.join(index_storage_dir, f) for f in (INDEX_FILE, "meta.pkl", "buffer.pkl", "cfg.json"))
 
 
 class Index:
-    def __init__(self, cfg: IndexCfg, engine_factory: Optional[Callable] = None):
+    def __init__(self, cfg: IndexCfg, engine_factory: Optional[Callable] = None, device: Optional[int] = None):
         self.cfg = cfg
-        self._engine_factory = engine_factory or default_engine_factory
+        # the GPU of the owning server rank, resolved ONCE here: training and adds run on threads
+        # started with _thread.start_new_thread, whose current CUDA device would be 0
+        self.device = device
+        if engine_factory is None:
+            if device is None:
+                try:
+                    import torch
+
+                    if torch.cuda.is_available():
+                        self.device = torch.cuda.current_device()
+                except Exception:
+                    pass
+            dev = self.device
+            self._engine_factory = lambda c: default_engine_factory(c, dev)
+        else:
+            self._engine_factory = engine_factory
+        self._stop_watcher = threading.Event()
         self.embeddings_buffer: List[np.ndarray] = []
         self.total_data = 0
         self.id_to_metadata: List[object] = []
         self._meta_arr = None  # object-array view of id_to_metadata, rebuilt lazily
+        self._meta_int_cache = None  # (len(id_to_metadata), int64 device table | None), see meta_int_table
+        self._filter_cols = {}  # filter_pos -> (len(id_to_metadata), int32 device codes, {value: code})
         self.buffer_lock = threading.Lock()
         self.index_lock = threading.Lock()
         self.state = IndexState.NOT_TRAINED
@@ -90,7 +137,17 @@ class Index:
             self._run_save_watcher()
 
     # ------------------------------------------------------------ ingest
+    def _bind_device(self):
+        """pin the calling thread to this shard's GPU (no-op for injected engines / no GPU)"""
+        if self.device is None:
+            return
+        import torch
+
+        if torch.cuda.is_available():
+            torch.cuda.set_device(self.device)
+
     def drop_index(self):
+        self._stop_watcher.set()
         with self.buffer_lock:
             self.embeddings_buffer, self.total_data, self.id_to_metadata = [], 0, []
             self._meta_arr = None
@@ -129,6 +186,7 @@ class Index:
         return buffered, indexed
 
     def train(self) -> None:
+        self._bind_device()
         with self.index_lock:
             if self.state != IndexState.NOT_TRAINED:
                 return
@@ -169,6 +227,7 @@ class Index:
             _thread.start_new_thread(self._add_buffer_to_idx, ())
 
     def _add_buffer_to_idx(self):
+        self._bind_device()
         try:
             while True:
                 with self.buffer_lock:
@@ -202,6 +261,96 @@ class Index:
                 embs = None
         return scores, self._ids_to_meta(ids), embs
 
+    # ---- the NCCL data plane (spmd.SearchPlane) drives the engine directly, under the same rules
+    def is_searchable(self) -> bool:
+        """caller holds index_lock; same condition as search() (reference index.py:247)"""
+        return self.state == IndexState.TRAINED and self.faiss_index is not None
+
+    def adopt_engine(self, engine, meta_table=None) -> None:
+        """Install a shard that was built directly on the device (bench / bulk loaders that cannot
+        afford host round trips): the engine becomes `faiss_index`, state TRAINED.  `meta_table`
+        (int64 device tensor, local id -> integer metadata) stands in for `id_to_metadata`."""
+        with self.buffer_lock, self.index_lock:
+            self.faiss_index = engine
+            self.state = IndexState.TRAINED
+            if meta_table is not None:
+                self.id_to_metadata = IntMetadata(meta_table)
+            self._meta_arr = None
+            self._meta_int_cache = None
+            self._filter_cols = {}
+
+    def meta_int_table(self, device):
+        """int64 device tensor `local id -> metadata` when EVERY metadata entry of this shard is a
+        non-negative integer (the convention of scripts/load_data.py:120-124), else None.  This is
+        the device form of the id -> metadata loop of the reference (index.py:260-268)."""
+        import torch
+
+        with self.buffer_lock:
+            n = len(self.id_to_metadata)
+            c = self._meta_int_cache
+            if c is not None and c[0] == n:
+                return c[1]
+            tab = None
+            if isinstance(self.id_to_metadata, IntMetadata):
+                tab = self.id_to_metadata.table.to(device)
+            else:
+                try:
+                    arr = np.asarray(self.id_to_metadata)
+                except ValueError:  # ragged tuples
+                    arr = None
+                if arr is not None and arr.ndim == 1 and arr.dtype.kind in "iu" and (n == 0 or arr.min() >= 0):
+                    tab = torch.from_numpy(arr.astype(np.int64)).to(device)
+            self._meta_int_cache = (n, tab)
+            return tab
+
+    def filter_column(self, filter_pos: int, filter_value, device):
+        """(int32 device codes of metadata[filter_pos] per local id, code of filter_value).
+        Code -2 = what the reference's post-filter skips outright (no metadata, or a tuple too short,
+        client.py:235-241); entries whose code equals the returned drop code are the ones with
+        metadata[filter_pos] == filter_value."""
+        import torch
+
+        with self.buffer_lock:
+            n = len(self.id_to_metadata)
+            c = self._filter_cols.get(filter_pos)
+            if c is None or c[0] != n:
+                codes = np.full(n, -2, dtype=np.int32)
+                vocab = c[2] if c is not None else {}
+                start = 0
+                if c is not None and c[0] < n:      # metadata only grows: extend the old column
+                    codes[:c[0]] = c[3]
+                    start = c[0]
+                for i in range(start, n):
+                    m = self.id_to_metadata[i]
+                    try:
+                        if m and len(m) > filter_pos:
+                            codes[i] = vocab.setdefault(m[filter_pos], len(vocab))
+                    except TypeError:               # no len() / unhashable value: never kept, never matched
+                        pass
+                c = (n, torch.from_numpy(codes).to(device), vocab, codes)
+                self._filter_cols[filter_pos] = c
+            try:
+                drop = c[2].get(filter_value, -1)
+            except TypeError:
+                drop = -1
+            return c[1], drop
+
+    def lookup_meta(self, local_ids) -> List[object]:
+        """metadata objects of shard-local ids (flat list; -1 -> None)"""
+        return self._ids_to_meta(np.asarray(local_ids, dtype=np.int64).reshape(-1))
+
+    def get_meta_kind(self) -> str:
+        """"int" when the integer fast path applies to this shard, else "object" """
+        with self.buffer_lock:
+            if isinstance(self.id_to_metadata, IntMetadata):
+                return "int"
+            try:
+                arr = np.asarray(self.id_to_metadata)
+            except ValueError:
+                return "object"
+            ok = arr.ndim == 1 and arr.dtype.kind in "iu" and (arr.size == 0 or arr.min() >= 0)
+            return "int" if ok else "object"
+
     def search_ids(self, query_batch: np.ndarray, top_k: int) -> Tuple[np.ndarray, np.ndarray]:
         """Same as search() but returns shard-local ids (used by the NCCL data plane)."""
         with self.index_lock:
@@ -212,6 +361,8 @@ class Index:
     def _ids_to_meta(self, ids: np.ndarray) -> List[List[object]]:
         # vectorised form of the reference's O(nq*k) double loop (index.py:260-268): -1 -> None
         with self.buffer_lock:
+            if isinstance(self.id_to_metadata, IntMetadata):
+                return self.id_to_metadata.lookup(ids)
             if self._meta_arr is None or self._meta_arr.shape[0] != len(self.id_to_metadata) + 1:
                 arr = np.empty(len(self.id_to_metadata) + 1, dtype=object)
                 arr[:-1] = self.id_to_metadata
@@ -308,16 +459,26 @@ class Index:
             return True
 
     def _run_save_watcher(self):
-        def loop(idx: "Index"):
-            while True:
-                time.sleep(idx.cfg.save_interval_sec)
-                idx._maybe_save(ignore_time=False)
+        import weakref
 
-        _thread.start_new_thread(loop, (self,))
+        # the watcher must not keep a dropped shard (and its HBM) alive: weak reference + stop flag
+        ref, stop, period = weakref.ref(self), self._stop_watcher, self.cfg.save_interval_sec
+
+        def loop():
+            while not stop.wait(period):
+                idx = ref()
+                if idx is None:
+                    return
+                idx._bind_device()
+                idx._maybe_save(ignore_time=False)
+                del idx
+
+        _thread.start_new_thread(loop, ())
 
     @classmethod
     def from_storage_dir(cls, index_storage_dir: str, cfg: IndexCfg = None, ignore_buffer: bool = True,
-                         engine_factory: Optional[Callable] = None) -> Union[None, "Index"]:
+                         engine_factory: Optional[Callable] = None, device: Optional[int] = None
+                         ) -> Union[None, "Index"]:
         index_file, meta_file, buffer_file, cfg_file = get_index_files(index_storage_dir)
         faiss_file = os.path.join(index_storage_dir, FAISS_INDEX_FILE)
         if not os.path.exists(index_file) and not os.path.exists(faiss_file):
@@ -332,7 +493,7 @@ class Index:
                 buffer = pickle.load(fh)
         if cfg is None:
             cfg = IndexCfg.from_json(cfg_file) if os.path.isfile(cfg_file) else IndexCfg()
-        result = cls(cfg, engine_factory=engine_factory)
+        result = cls(cfg, engine_factory=engine_factory, device=device)
         # builder type / sizes come from the cfg stored next to the index when the caller's cfg lacks them
         build_cfg = cfg
         if not cfg.index_builder_type and os.path.isfile(cfg_file):

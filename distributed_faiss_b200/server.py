@@ -27,7 +27,8 @@ logger = logging.getLogger("distributed_faiss_b200")
 
 
 class IndexServer:
-    def __init__(self, rank: int, index_storage_dir, engine_factory: Optional[Callable] = None):
+    def __init__(self, rank: int, index_storage_dir, engine_factory: Optional[Callable] = None,
+                 device: Optional[int] = None):
         self.indexes = {}
         self.indexes_lock = threading.Lock()
         self.rank = rank
@@ -35,16 +36,29 @@ class IndexServer:
         self.index_storage_dir = index_storage_dir
         self._engine_factory = engine_factory
         self._stopping = False
+        # GPU ordinal of this rank; settable before the first index is created (one process that
+        # hosts several server ranks on one GPU, e.g. the 1-GPU point of the scaling curve)
+        self.device = device
 
     # ------------------------------------------------------------ device pinning
-    def _bind_device(self):
-        """rank r -> GPU r (mod visible devices); a no-op when an engine factory is injected."""
+    def _device(self):
+        """rank r -> GPU r (mod visible devices); None when an engine factory is injected / no GPU"""
         if self._engine_factory is not None:
-            return
+            return None
         import torch
 
-        if torch.cuda.is_available():
-            torch.cuda.set_device(self.rank % torch.cuda.device_count())
+        if not torch.cuda.is_available():
+            return None
+        if self.device is None:
+            self.device = self.rank % torch.cuda.device_count()
+        return self.device
+
+    def _bind_device(self):
+        dev = self._device()
+        if dev is not None:
+            import torch
+
+            torch.cuda.set_device(dev)
 
     # ------------------------------------------------------------ service loop
     def start_blocking(self, port=DEFAULT_PORT, v6=False, load_index=False):
@@ -125,7 +139,7 @@ class IndexServer:
         with self.indexes_lock:
             if index_id in self.indexes:
                 return False
-            self.indexes[index_id] = Index(cfg, engine_factory=self._engine_factory)
+            self.indexes[index_id] = Index(cfg, engine_factory=self._engine_factory, device=self._device())
             return True
 
     def add_index_data(self, index_id: str, embeddings: np.ndarray, metadata: Optional[List[object]] = None,
@@ -146,6 +160,22 @@ class IndexServer:
 
     def search_ids(self, index_id: str, query_batch: np.ndarray, top_k: int):
         return self._get_index(index_id).search_ids(query_batch, top_k)
+
+    # ---- support of the NCCL data plane (spmd.SearchPlane); control-plane calls, not timed
+    def adopt_index(self, index_id: str, cfg: IndexCfg, engine, meta_table=None) -> None:
+        """register a shard built directly on this rank's GPU (in-process callers only)"""
+        self._bind_device()
+        cfg.index_storage_dir = self._get_storage_dir(index_id, cfg)
+        index = Index(cfg, engine_factory=self._engine_factory, device=self._device())
+        index.adopt_engine(engine, meta_table)
+        with self.indexes_lock:
+            self.indexes[index_id] = index
+
+    def get_meta_kind(self, index_id: str) -> str:
+        return self._get_index(index_id).get_meta_kind()
+
+    def lookup_meta(self, index_id: str, local_ids) -> List[object]:
+        return self._get_index(index_id).lookup_meta(local_ids)
 
     def get_centroids(self, index_id: str):
         return self._get_index(index_id).get_centroids()
@@ -181,7 +211,9 @@ class IndexServer:
 
     def drop_index(self, index_id: str):
         with self.indexes_lock:
-            self.indexes.pop(index_id, None)
+            index = self.indexes.pop(index_id, None)
+        if index is not None:
+            index.drop_index()  # releases the engine (HBM) and stops the save watcher
 
     def save_index(self, index_id: str):
         with self.indexes_lock:
@@ -200,7 +232,8 @@ class IndexServer:
                 if cfg:
                     self.indexes[index_id].upd_cfg(cfg)
                 return True
-            index = Index.from_storage_dir(index_dir, cfg, engine_factory=self._engine_factory)
+            index = Index.from_storage_dir(index_dir, cfg, engine_factory=self._engine_factory,
+                                           device=self._device())
             if index is None:
                 return False
             self.indexes[index_id] = index

@@ -99,6 +99,15 @@ int dfx_search_dev(dfx_index *idx, int64_t nq, const float *d_x, int64_t k, floa
 /* faiss_index.search_and_reconstruct: decode rows by id (index.py:255); id -1 -> NaN row */
 int dfx_reconstruct(dfx_index *idx, int64_t n, const int64_t *ids, float *out);
 
+/* device form, for winners that travelled through the all-gather + merge (client.py:287-289,
+ * 299-307 carry per-shard embeddings to the client; here only the WINNERS are decoded, by the
+ * shard that owns them).  shard_tag < 0: d_ids are shard-local ids, as dfx_reconstruct.
+ * shard_tag >= 0: d_ids are exchange ids (dfx_encode_ids_dev); rows owned by another shard (or
+ * empty, -1) are left untouched, so every rank decodes into a zeroed [n, d] buffer and the
+ * buffers are summed. */
+int dfx_reconstruct_dev(dfx_index *idx, int64_t n, const int64_t *d_ids, int64_t shard_tag,
+                        float *d_out, void *stream);
+
 /* ---- attributes the wrapper touches: .nprobe (index.py:356,495) .ntotal (index.py:184)
  *      .nlist / .quantizer.reconstruct_n(0, nlist) (index.py:350) ---- */
 int dfx_set_nprobe(dfx_index *idx, int64_t nprobe);
@@ -118,6 +127,27 @@ int dfx_merge(int64_t S, int64_t nq, int64_t k, const float *D, const int64_t *I
               float *outD, int64_t *outI);
 int dfx_merge_dev(int64_t S, int64_t nq, int64_t k, const float *d_D, const int64_t *d_I,
                   int negate, float *d_outD, int64_t *d_outI, void *stream);
+
+/* the same merge over what ONE all-gather of the ranks' result blocks delivers: rank r's block
+ * starts at d_packed + r * rank_stride_bytes and holds D f32[S_loc][nq][k] at offset 0 and
+ * I i64[S_loc][nq][k] at off_I_bytes (both multiples of 8).  Shard s = r * S_loc + j. */
+int dfx_merge_packed_dev(int64_t R, int64_t S_loc, int64_t nq, int64_t k, const void *d_packed,
+                         int64_t rank_stride_bytes, int64_t off_I_bytes, int negate,
+                         float *d_outD, int64_t *d_outI, void *stream);
+
+/* shard-local ids -> exchange ids: out = ids < 0 ? -1 : (shard_tag << 40) | ids, so that the
+ * client can tell which (shard, local id) won after the merge (the reference's synthetic
+ * positions, client.py:288).  d_col (optional): one int32 code per local id for ONE metadata
+ * position (-2 = no metadata / tuple too short); entries whose code == drop_code or -2 are what
+ * search_with_filter's post-filter drops (client.py:235-243) and get bit 62 set. */
+int dfx_encode_ids_dev(int64_t n, const int64_t *d_ids, int64_t shard_tag, const int32_t *d_col,
+                       int32_t drop_code, int64_t *d_out, void *stream);
+/* search_with_filter's post-filter on device (client.py:229-250): per query, walk the k_in merged
+ * slots in rank order, keep existing entries without the drop flag, stop at k_out; pads
+ * (FLT_MAX, -1); d_count[q] = number kept. */
+int dfx_filter_compact_dev(int64_t nq, int64_t k_in, int64_t k_out, const float *d_D,
+                           const int64_t *d_I, float *d_outD, int64_t *d_outI, int32_t *d_count,
+                           void *stream);
 
 /* map shard-local ids to caller ids on device: out[i] = ids[i] < 0 ? -1 : table[ids[i]]
  * (the device form of Index.search's id -> metadata loop, index.py:260-268, for the

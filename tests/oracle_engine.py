@@ -36,26 +36,74 @@ def oracle_merge(Dall, Iall, negate):
 
 
 class OracleBackend:
-    """spmd.ShardGroup backend on CPU tensors (gloo tests)."""
+    """spmd.ShardGroup / SearchPlane backend on CPU tensors (gloo tests): the device operations of
+    spmd.CudaBackend restated with the oracle and numpy."""
 
     name = "oracle"
 
-    def search(self, shard, x_t, k):
+    def search_local(self, shard, x_t, k, D_out, I_out):
         import torch
 
         D, I = shard.search(x_t.numpy(), k)
-        return torch.from_numpy(D), torch.from_numpy(I)
+        D_out.copy_(torch.from_numpy(D))
+        I_out.copy_(torch.from_numpy(I))
 
-    def search_into(self, shard, x_t, k, D_out, I_out, table_t):
-        D, I = self.search(shard, x_t, k)
-        D_out.copy_(D)
-        I_out.copy_(I if table_t is None else self.map_ids(I, table_t))
-
-    def map_ids(self, ids_t, table_t):
+    def map_ids(self, ids_t, table_t, out_t=None):
         import torch
 
         out = table_t[ids_t.clamp(min=0)]
-        return torch.where(ids_t < 0, torch.full_like(out, -1), out)
+        out = torch.where(ids_t < 0, torch.full_like(out, -1), out)
+        if out_t is not None:
+            out_t.copy_(out)
+            return out_t
+        return out
+
+    def encode_ids(self, ids_t, tag, out_t, col_t=None, drop_code=-1):
+        import torch
+
+        e = (int(tag) << 40) | ids_t.clamp(min=0)
+        if col_t is not None:
+            c = col_t[ids_t.clamp(min=0)]
+            e = torch.where((c == drop_code) | (c == -2), e | (1 << 62), e)
+        out_t.copy_(torch.where(ids_t < 0, torch.full_like(e, -1), e))
+        return out_t
+
+    def merge_packed(self, packed_t, R, S_loc, nq, k, stride, off_I, negate):
+        import torch
+
+        raw = packed_t.numpy()
+        n = S_loc * nq * k
+        Ds, Is = [], []
+        for r in range(R):
+            blk = raw[r * stride:(r + 1) * stride]
+            Ds.append(blk[:4 * n].view(np.float32).reshape(S_loc, nq, k))
+            Is.append(blk[off_I:off_I + 8 * n].view(np.int64).reshape(S_loc, nq, k))
+        D, I = oracle_merge(np.concatenate(Ds), np.concatenate(Is), negate)
+        return torch.from_numpy(D), torch.from_numpy(I)
+
+    def filter_compact(self, D_t, I_t, k_out):
+        import torch
+
+        D, I = D_t.numpy(), I_t.numpy()
+        nq = D.shape[0]
+        oD = np.full((nq, k_out), np.finfo(np.float32).max, dtype=np.float32)
+        oI = np.full((nq, k_out), -1, dtype=np.int64)
+        cnt = np.zeros(nq, dtype=np.int32)
+        for q in range(nq):
+            keep = [j for j in range(D.shape[1]) if I[q, j] >= 0 and not (I[q, j] >> 62) & 1][:k_out]
+            oD[q, :len(keep)] = D[q, keep]
+            oI[q, :len(keep)] = I[q, keep]
+            cnt[q] = len(keep)
+        return torch.from_numpy(oD), torch.from_numpy(oI), torch.from_numpy(cnt)
+
+    def reconstruct_owned(self, shard, I_t, R_t, tag):
+        import torch
+
+        I = I_t.numpy().reshape(-1)
+        own = (I >= 0) & (((I >> 40) & 0xFFFFF) == tag)
+        if own.any():
+            rows = shard.reconstruct_rows(I[own] & ((1 << 40) - 1))
+            R_t.view(-1, R_t.shape[-1])[torch.from_numpy(np.nonzero(own)[0])] = torch.from_numpy(rows)
 
     def merge(self, D_t, I_t, negate):
         import torch
