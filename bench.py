@@ -214,32 +214,57 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------
-def make_cpu_oracle(shard_idx_obj):
-    """ship ONE shard (codes, ids, centroids, codebooks) to the host and wrap it in the oracle"""
-    from oracle import oracle as O
+def make_cpu_baseline(shard_idx_obj, threads):
+    """ship ONE shard (codes, ids, centroids, codebooks) to the host: the timed CPU baseline
+    (oracle/cpu_baseline.py: sgemm coarse + threaded scan) and the bit-exact checker share the state"""
+    from oracle import cpu_baseline as CB
 
     st = shard_idx_obj.get_state()
-    o = O.OracleIVFPQ(D, st["nlist"], PQ_M, 8, coarse_metric=O.METRIC_L2)
-    o.set_state(st, recompute_tvals=False)
-    return o
+    return CB.CpuIVFPQ(st, threads=threads), st
 
 
-def cpu_baseline(o, xq_np, nprobe, nq_cpu, n_shards_total, warm=True):
-    """The reference's CPU path (oracle restatement), all host threads, on ONE shard of the
-    workload; system QPS = shard QPS / n_shards (the same host serves every shard)."""
+def check_against_oracle(st, shard, xq_np, nprobe, nq_check):
+    """bit-exact parity of one GPU shard against the CHECKER oracle on a query sample"""
     from oracle import oracle as O
 
+    o = O.OracleIVFPQ(D, st["nlist"], PQ_M, 8, coarse_metric=O.METRIC_L2)
+    o.set_state(st, recompute_tvals=False)
     o.nprobe = nprobe
-    q = xq_np[:nq_cpu]
-    if warm:
-        o.search(q[:32], K)
-    t0 = time.perf_counter()
+    q = xq_np[:nq_check]
     Do, Io = o.search(q, K)
-    dt = time.perf_counter() - t0
-    return {"value": (len(q) / dt) / n_shards_total, "unit": "QPS", "cores": O.num_threads(), "kind": "port",
-            "sample": f"shard 0 of {n_shards_total} ({o.ntotal} vectors, nlist {o.nlist}), {len(q)} queries, "
-                      f"nprobe {nprobe}, {dt:.2f} s; system QPS = shard QPS / {n_shards_total}",
-            "_D": Do, "_I": Io}
+    shard.nprobe = nprobe
+    Dg, Ig = shard.search(q, K)
+    return bool(np.array_equal(Dg, Do) and np.array_equal(Ig, Io))
+
+
+def time_cpu(cb, xq_np, nprobe, batch, min_seconds, n_shards_total, offset=0):
+    """one timed sample of the CPU baseline: whole batches of `batch` queries against ONE shard of
+    the workload until `min_seconds` have passed; system QPS = shard QPS / n_shards (the same host
+    serves every shard)"""
+    nb = max(1, (xq_np.shape[0] - batch) // batch + 1)
+    done, t0, it = 0, time.perf_counter(), 0
+    while True:
+        off = ((offset + it) % nb) * batch
+        cb.search(xq_np[off:off + batch], K, nprobe)
+        done += batch
+        it += 1
+        dt = time.perf_counter() - t0
+        if dt >= min_seconds:
+            break
+    return (done / dt) / n_shards_total, dt, done
+
+
+def free_ports(n):
+    import socket
+
+    socks = [socket.socket() for _ in range(n)]
+    try:
+        for s_ in socks:
+            s_.bind(("127.0.0.1", 0))
+        return [s_.getsockname()[1] for s_ in socks]
+    finally:
+        for s_ in socks:
+            s_.close()
 
 
 def main():
@@ -252,7 +277,7 @@ def main():
     ap.add_argument("--batch", type=int, default=4096)
     ap.add_argument("--nprobe", type=int, default=0, help="0 = smallest power of two reaching the recall gate")
     ap.add_argument("--nlist", type=int, default=0)
-    ap.add_argument("--nq-pool", type=int, default=10000)
+    ap.add_argument("--nq-pool", type=int, default=12288)
     ap.add_argument("--kmeans-niter", type=int, default=10)
     ap.add_argument("--train-pts", type=int, default=64, help="training points per centroid")
     ap.add_argument("--clusters", type=int, default=1, help="generator cluster centres (1 = one smooth distribution)")
@@ -263,12 +288,9 @@ def main():
     ap.add_argument("--rank-dim", type=int, default=16)
     ap.add_argument("--sigma", type=float, default=1.0)
     ap.add_argument("--sigma-q", type=float, default=0.02)
-    ap.add_argument("--cpu-queries", type=int, default=512)
+    ap.add_argument("--cpu-seconds", type=float, default=2.0, help="minimum CPU time of one timed CPU sample")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--sweep", action="store_true", help="also time batch sizes 1, 64, 512")
-    ap.add_argument("--variant-sweep", action="store_true",
-                    help="also time the experimental kernel variants on the already built shards "
-                         "(scan_variant 2 / 3, prep_variant 2) and check that they return the same ids")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the query-batch sweep 1/8/64/512/4096")
     args = ap.parse_args()
 
     import torch
@@ -289,7 +311,6 @@ def main():
     assert NSHARDS % world == 0, "--gpus must divide 8"
     dist = torch.distributed
     nvec = args.nvec
-    n_shard0 = sum(n for _, n in shard_rows(nvec, 0))
     C = max(1, args.clusters)
     G = max(C, (nvec // args.group_size) // C * C)      # rows i, i+G, i+2G, ... form a group
     synth = engine.Synth(1234, D, args.rank_dim, C, args.sigma, args.sigma_q, ngroups=G, eps=args.eps,
@@ -316,43 +337,96 @@ def main():
         infos.append(info)
         log(f"shard {s}: {info}")
     build_s = time.time() - t_build0
-    group = spmd.ShardGroup(shards, tables)
-    gt, gt_viol, gt_ok = None, 0, None
-    if gtc is not None:
-        gt_viol = gtc.finish(world, dist)
-        gt, gt_ok = gtc.gt, gtc.certified
-        log(f"ground truth: {n_eval} queries, {gt_viol} uncertified")
 
-    def run_search(x, nprobe):
-        group.set_nprobe(nprobe)
-        return group.search(x, K, maximize=False)
-
-    # ---------------- reference arm: CPU only
+    # ---------------- reference arm: the CPU baseline alone (the shard was built on the GPU and
+    # exported to the host; nothing of libdfx runs inside the timed region)
     if args.impl == "reference":
-        # same nprobe as the GPU arm's recall gate selects for this size (measured: bench logs in
-        # profiles/; the GPU arm re-measures and reports its own value in config.nprobe)
+        from oracle import cpu_baseline as CB
+
         nprobe = args.nprobe or (8 if nvec >= 500_000_000 else 4)
+        threads = CB.host_threads()
         xq_np = xq.cpu().numpy()
-        orc = make_cpu_oracle(shards[0])
-        log("shard 0 exported to the host oracle")
+        cb, st = make_cpu_baseline(shards[0], threads)
+        log(f"shard 0 exported to the host; CPU baseline on {cb.threads} threads ({CB._lib_kind} build)")
+        B = args.batch
+        # agreement with the GPU / checker on this shard (the GPU arm measures recall with this nprobe)
+        shards[0].nprobe = nprobe
+        Dg, Ig = shards[0].search(xq_np[:512], K)
+        Dc, Ic = cb.search(xq_np[:512], K, nprobe)
+        agree = float((Ic == Ig).mean())
         vals = []
         for it in range(args.warmup + args.steps):
-            off = (it * args.cpu_queries) % max(1, args.nq_pool - args.cpu_queries)
-            cb = cpu_baseline(orc, xq_np[off:], nprobe, args.cpu_queries, NSHARDS, warm=(it == 0))
+            v, dt, done = time_cpu(cb, xq_np, nprobe, B, args.cpu_seconds, NSHARDS, offset=it)
             if it >= args.warmup:
-                vals.append(cb["value"])
-        cb.pop("_D"), cb.pop("_I")
-        v = float(np.mean(vals))
-        cb["value"] = v
+                vals.append(v)
+        v = float(np.median(vals))
+        cbj = {"value": v, "unit": "QPS", "cores": cb.threads, "kind": "port",
+               "sample": f"shard 0 of {NSHARDS} ({cb.ntotal} vectors, nlist {cb.nlist}), batches of {B} queries, nprobe "
+                         f"{nprobe}, >= {args.cpu_seconds:g} s per timed sample, median of {len(vals)}; "
+                         f"system QPS = shard QPS / {NSHARDS}",
+               "implementation": "oracle/cpu_ivfpq.c: MKL sgemm coarse quantizer + OpenMP table build / list scan "
+                                 f"({CB._lib_kind} build); NOT the scalar bit-exact checker",
+               "spread": float((max(vals) - min(vals)) / v) if v else None,
+               "ids_equal_gpu_shard": agree, "setup": "shard 0 built by libdfx on GPU 0 and exported; timed region is CPU only"}
         out = {"impl": "reference", "metric": "QPS at recall@10>=0.95, IVF-PQ d=128", "value": v, "unit": "QPS",
                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-               "ms_per_step": 1e3 * args.cpu_queries / (v * NSHARDS) if v else None,
+               "ms_per_step": 1e3 * B / v if v else None,
                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-               "config": {"workload": workload_name(nvec), "nprobe": nprobe, "batch": args.cpu_queries},
-               "cpu_baseline": cb,
+               "config": {"workload": workload_name(nvec), "nvec": nvec, "shards": NSHARDS, "nprobe": nprobe, "batch": B,
+                          "k": K, "nprobe_source": "the recall gate of the GPU arm on the same index (config.nprobe there)"},
+               "cpu_baseline": cbj,
                "e2e": {"value": v, "unit": "QPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(out), flush=True)
         return 0
+
+    gt, gt_viol, gt_ok = None, 0, None
+    gt_viol = gtc.finish(world, dist)
+    gt, gt_ok = gtc.gt, gtc.certified
+    log(f"ground truth: {n_eval} queries, {gt_viol} uncertified")
+
+    # ---------------- the reference's process model on this box: one IndexServer per shard (rank r
+    # hosts servers r*s_loc ...), their control sockets, the NCCL search plane over them, and ONE
+    # IndexClient in the process of rank 0.  Ranks != 0 serve until rank 0 stops the plane.
+    import tempfile
+    import threading
+
+    from distributed_faiss_b200.client import IndexClient
+    from distributed_faiss_b200.index_cfg import IndexCfg
+    from distributed_faiss_b200.server import IndexServer
+
+    store = tempfile.mkdtemp(prefix="dfx_bench_")
+    ports = free_ports(s_loc)
+    servers = []
+    for j, s in enumerate(my_shards):
+        srv = IndexServer(s, store, device=torch.cuda.current_device())
+        cfg = IndexCfg(index_builder_type="knnlm", dim=D, metric="l2", centroids=infos[j]["nlist"], code_size=PQ_M)
+        srv.adopt_index("bench", cfg, shards[j], tables[j])
+        threading.Thread(target=srv.start_blocking, args=(ports[j],), daemon=True).start()
+        servers.append(srv)
+    plane = spmd.SearchPlane(servers)
+    all_ports = [None] * world
+    if world > 1:
+        dist.all_gather_object(all_ports, ports)
+    else:
+        all_ports = [ports]
+    if rank != 0:
+        plane.serve_forever()
+        dist.barrier()
+        dist.destroy_process_group()
+        return 0
+
+    disc = os.path.join(store, "servers.txt")
+    with open(disc, "w") as fh:
+        flat = [p_ for pr in all_ports for p_ in pr]
+        fh.write(f"{len(flat)}\n" + "".join(f"127.0.0.1,{p_}\n" for p_ in flat))
+    client = IndexClient(disc)
+    client.cfg = IndexCfg(index_builder_type="knnlm", dim=D, metric="l2")
+    assert client.plane is plane, "IndexClient did not attach to the NCCL search plane"
+
+    def search_dev(x_t):
+        """device-resident form of IndexClient.search (inputs already in HBM): the collective only"""
+        o = plane.search("bench", x_t, K, maximize=False, int_meta=True)
+        return o.D, o.I
 
     # ---------------- nprobe: smallest power of two meeting the recall gate
     recalls = {}
@@ -361,54 +435,47 @@ def main():
         for cand in (1, 2, 4, 8, 16, 32, 64, 128, 256, 512):
             if cand > shards[0].nlist:
                 break
-            _, I = run_search(xq[:n_eval].contiguous(), cand)
+            client.set_nprobe("bench", cand)
+            _, I = search_dev(xq[:n_eval].contiguous())
             recalls[cand] = recall_at_k(I, gt, gt_ok)
             log(f"nprobe {cand}: recall@10 = {recalls[cand]:.4f}")
             nprobe = cand
             if recalls[cand] >= 0.95:
                 break
-    _, I = run_search(xq[:n_eval].contiguous(), nprobe)
+    client.set_nprobe("bench", nprobe)
+    _, I = search_dev(xq[:n_eval].contiguous())
     log(f"nprobe = {nprobe}")
     recall = recall_at_k(I, gt, gt_ok)
+    recall_all = recall_at_k(I, gt, None)
     r1 = float((I[:, :1] == gt[:, :1])[gt_ok].float().mean().item())
 
-    # ---------------- timed region (device-resident inputs)
-    B = args.batch
-    nb = max(1, args.nq_pool // B)
-    batches = [xq[i * B:(i + 1) * B].contiguous() for i in range(nb)] if B <= args.nq_pool else [xq.repeat((B // args.nq_pool) + 1, 1)[:B].contiguous()]
+    # ---------------- timed regions
+    def batches_of(b):
+        nb = max(1, args.nq_pool // b)
+        if b <= args.nq_pool:
+            return [xq[i * b:(i + 1) * b].contiguous() for i in range(min(nb, 64))]
+        return [xq.repeat((b // args.nq_pool) + 1, 1)[:b].contiguous()]
 
     def timed(batches_, steps, warmup, host=False):
+        """K steps bracketed by device events on EVERY rank (plane.timer_*), max over ranks"""
         host_batches = [b.cpu().numpy() for b in batches_] if host else None
+        run = (lambda i: client.search(host_batches[i % len(batches_)], K, "bench")) if host else \
+              (lambda i: search_dev(batches_[i % len(batches_)]))
         for it in range(warmup):
-            if host:
-                group.search_host(host_batches[it % len(batches_)], K)
-            else:
-                group.search(batches_[it % len(batches_)], K)
+            run(it)
         torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
+        plane.timer_start()
         for it in range(steps):
-            if host:
-                group.search_host(host_batches[it % len(batches_)], K)
-            else:
-                group.search(batches_[it % len(batches_)], K)
-        e1.record()
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item())
+            run(it)
+        return plane.timer_stop()
 
-    group.set_nprobe(nprobe)
-    # ndis per batch (untimed) for the roofline's algorithmic bytes
+    B = args.batch
+    batches = batches_of(B)
+    # ndis per batch (untimed) for the roofline's algorithmic bytes: this rank's shards
     ndis_per_batch = []
     for b in batches:
-        group.search(b, K)
+        search_dev(b)
+        torch.cuda.synchronize()
         ndis_per_batch.append(sum(s.last_stats()["ndis"] for s in shards))
     for s in shards:
         s.profile(True)
@@ -420,63 +487,44 @@ def main():
     ms = timed(batches, args.steps, args.warmup)
     torch.cuda.profiler.stop()
     launches = engine.launch_count() - launches0
-    clk = clocks.stop()
     scan_ms, scan_launches = 0.0, 0
     for s in shards:
         m, n = s.profile_read(reset=True)
         scan_ms += m
         scan_launches += n
         s.profile(False)
-    # the profile covers warm-up + timed launches alike; per-launch averages are what is used
     qps = args.steps * B / (ms / 1e3)
     ndis_step = float(np.mean([ndis_per_batch[it % len(batches)] for it in range(args.steps)]))
     launches_timed = launches * args.steps // (args.steps + args.warmup)
-
     log(f"timed region done: {ms / args.steps:.3f} ms/step")
-    # e2e: host buffers through the public call, H2D + D2H inside the timed region
+
+    # e2e: IndexClient.search with HOST buffers -- pinned staging, H2D, the collective, one D2H,
+    # integer metadata rows -- i.e. the call a user of the reference makes
     ms_e2e = timed(batches, args.steps, args.warmup, host=True)
+    clk = clocks.stop()
     qps_e2e = args.steps * B / (ms_e2e / 1e3)
+    log(f"e2e done: {ms_e2e / args.steps:.3f} ms/step")
 
-    sweep = {}
-    if args.sweep:
-        for b in (1, 64, 512):
-            bb = [xq[i * b:(i + 1) * b].contiguous() for i in range(min(32, args.nq_pool // b))]
-            st = max(args.steps, 50 if b <= 64 else args.steps)
-            t = timed(bb, st, args.warmup)
-            sweep[str(b)] = st * b / (t / 1e3)
+    # the same client through the reference's socket fan-out returns the same answer
+    hb = batches[0][:64].cpu().numpy()
+    Dp, Mp = client.search(hb, K, "bench")
+    client.detach_plane()
+    Ds, Ms = client.search(hb, K, "bench")
+    client.plane = plane
+    plane_equals_socket = bool(np.array_equal(Dp, Ds) and Mp == Ms)
 
-    variants = {}
-    if args.variant_sweep:
-        # experimental kernels on the same shards: convert the block layout in place, time the same
-        # batches, compare the ids of one batch with the default kernels' (they must be identical)
-        ref_D, ref_I = group.search(batches[0], K)
-        ref_I = ref_I.clone()
-        for sh in shards:
-            sh.set_param("scan_ring", 0)
-        for label, sv, pv, rv in (("scan2", 2, 1, 1), ("scan2+ring", 2, 1, 1), ("scan2+prep2", 2, 2, 1), ("scan2+prep2+rerank2", 2, 2, 2),
-                                  ("scan3", 3, 1, 1), ("rerank2", 1, 1, 2), ("default", 1, 1, 1)):
-            for sh in shards:
-                sh.set_param("scan_variant", sv)
-                sh.set_param("prep_variant", pv)
-                sh.set_param("rerank_variant", rv)
-                sh.set_param("scan_ring", 1 if label.endswith("+ring") else 0)
-            _, I_v = group.search(batches[0], K)
-            same = bool(torch.equal(I_v, ref_I))
-            for sh in shards:
-                sh.profile(True)
-                sh.profile_read(reset=True)
-            t = timed(batches, args.steps, args.warmup)
-            sm, sn = 0.0, 0
-            for sh in shards:
-                m_, n_ = sh.profile_read(reset=True)
-                sm += m_
-                sn += n_
-                sh.profile(False)
-            variants[label] = {"qps": args.steps * B / (t / 1e3), "ms_per_step": t / args.steps,
-                               "scan_ms_per_launch": sm / max(sn, 1), "ids_equal_default": same}
-            log(f"variant {label}: {variants[label]}")
+    sweep, sweep_e2e = {}, {}
+    if not args.no_sweep:
+        for b in (1, 8, 64, 512, 4096):
+            bb = batches_of(b)
+            st_ = max(args.steps, 100 if b <= 64 else args.steps)
+            t = timed(bb, st_, args.warmup)
+            sweep[str(b)] = st_ * b / (t / 1e3)
+            t = timed(bb, st_, args.warmup, host=True)
+            sweep_e2e[str(b)] = st_ * b / (t / 1e3)
+        log(f"sweep: {sweep}")
 
-    # roofline of the dominant kernel (scan_pq): algorithmic bytes = ndis * code_bytes
+    # roofline of the dominant kernel: algorithmic bytes = ndis * code_bytes
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -487,7 +535,6 @@ def main():
     per_launch_ms = scan_ms / max(scan_launches, 1)
     # this rank's launches cover its local shards; bytes per launch = ndis of one shard-search
     bytes_per_launch = (ndis_step / max(len(shards), 1)) * PQ_M
-    # (chunked searches split a batch into several launches; account for that)
     launches_per_search = max(1, round(scan_launches / max((args.steps + args.warmup) * len(shards), 1)))
     bytes_per_launch /= launches_per_search
     achieved = bytes_per_launch / (per_launch_ms * 1e-3) / 1e9 if per_launch_ms > 0 else 0.0
@@ -495,54 +542,69 @@ def main():
     # DRAM traffic of the same kernel from the committed ncu --set full capture (same command)
     traffic = None
     try:
-        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_scan_traffic.json")))
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r02_scan_traffic.json")))
         if tr["when"] == {"nvec": nvec, "batch": B, "nprobe": nprobe} and world == 1:
             traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
     except Exception:
         pass
-    roofline = {"kernel": "scan_pq_il_kernel (IVF-PQ list scan, interleaved M=32)", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    roofline = {"kernel": "scan_pq_il2_kernel (IVF-PQ table build + list scan, block-interleaved M=32)", "bound": "hbm",
+                "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "bytes_per_launch": bytes_per_launch, "ms_per_launch": per_launch_ms,
                 "launches_per_step": scan_launches / (args.steps + args.warmup),
                 "scan_share_of_step": scan_ms_per_step / (ms / args.steps) if ms else None}
 
-    log("e2e + sweep done")
     cb = None
-    if rank == 0 and world == 1 and not args.no_cpu:
-        cb = cpu_baseline(make_cpu_oracle(shards[0]), xq.cpu().numpy(), nprobe, args.cpu_queries, NSHARDS)
-        # cross-check on the way: the GPU shard and the oracle agree bit for bit on this sample
-        shards[0].nprobe = nprobe
-        Dg, Ig = shards[0].search(xq[:args.cpu_queries].cpu().numpy(), K)
-        Do_, Io_ = cb.pop("_D"), cb.pop("_I")
-        cb["gpu_equals_oracle"] = bool(np.array_equal(Dg, Do_) and np.array_equal(Ig, Io_))
+    if world == 1 and not args.no_cpu:
+        from oracle import cpu_baseline as CB
 
-    log("cpu baseline done")
-    if rank == 0:
-        out = {
-            "metric": "QPS at recall@10>=0.95, IVF-PQ d=128", "value": qps, "unit": "QPS", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "f32 (u8 PQ codes, f32 tables/accumulate)",
-            "data": "synthetic",
-            "config": {"workload": workload_name(nvec), "nvec": nvec, "shards": NSHARDS, "shards_per_gpu": s_loc,
-                       "nlist_per_shard": infos[0]["nlist"], "pq": "M=32 x 8 bit", "k": K, "nprobe": nprobe,
-                       "batch": B, "recall_at_10": recall, "recall_1_at_1": r1, "recall_by_nprobe": recalls,
-                       "gt_uncertified_queries": gt_viol, "l2_flush": "working set (PQ codes) >> 126 MB L2",
-                       "generator": {"clusters": C, "groups": G, "group_size": args.group_size, "rank": args.rank_dim,
-                                     "sigma": args.sigma, "delta": args.delta, "eps": args.eps, "sigma_q": args.sigma_q},
-                       "train": {"kmeans_niter": args.kmeans_niter, "points_per_centroid": args.train_pts},
-                       "build_seconds": build_s, "ndis_per_step": ndis_step},
-            "e2e": {"value": qps_e2e, "unit": "QPS", "h2d_bytes_per_step": B * D * 4, "d2h_bytes_per_step": B * K * 12,
-                    "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": int(launches_timed),
-            "clocks": clk,
-            "roofline": roofline,
-            "cpu_baseline": cb,
-        }
-        if sweep:
-            out["config"]["qps_by_batch"] = sweep
-        if variants:
-            out["config"]["experimental_variants"] = variants
-        print(json.dumps(out), flush=True)
+        xq_np = xq.cpu().numpy()
+        cbo, st = make_cpu_baseline(shards[0], CB.host_threads())
+        cbo.search(xq_np[:256], K, nprobe)   # warm
+        vals = [time_cpu(cbo, xq_np, nprobe, B, args.cpu_seconds, NSHARDS, offset=i)[0] for i in range(5)]
+        v = float(np.median(vals))
+        cb = {"value": v, "unit": "QPS", "cores": cbo.threads, "kind": "port",
+              "sample": f"shard 0 of {NSHARDS} ({cbo.ntotal} vectors, nlist {cbo.nlist}), batches of {B} queries, "
+                        f"nprobe {nprobe}, >= {args.cpu_seconds:g} s per timed sample, median of 5; "
+                        f"system QPS = shard QPS / {NSHARDS}",
+              "implementation": "oracle/cpu_ivfpq.c: MKL sgemm coarse quantizer + OpenMP table build / list scan "
+                                f"({CB._lib_kind} build); NOT the scalar bit-exact checker",
+              "spread": float((max(vals) - min(vals)) / v) if v else None}
+        # cross-check on the way: the GPU shard and the CHECKER oracle agree bit for bit on a sample
+        cb["gpu_equals_oracle"] = check_against_oracle(st, shards[0], xq_np, nprobe, 256)
+        del cbo, st
+        log("cpu baseline done")
+
+    out = {
+        "metric": "QPS at recall@10>=0.95, IVF-PQ d=128", "value": qps, "unit": "QPS", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32 (u8 PQ codes, f32 tables/accumulate)",
+        "data": "synthetic",
+        "config": {"workload": workload_name(nvec), "nvec": nvec, "shards": NSHARDS, "shards_per_gpu": s_loc,
+                   "nlist_per_shard": infos[0]["nlist"], "pq": "M=32 x 8 bit", "k": K, "nprobe": nprobe,
+                   "batch": B, "recall_at_10": recall, "recall_at_10_all_queries": recall_all, "recall_1_at_1": r1,
+                   "recall_by_nprobe": recalls,
+                   "gt_uncertified_queries": gt_viol, "l2_flush": "working set (PQ codes) >> 126 MB L2",
+                   "generator": {"clusters": C, "groups": G, "group_size": args.group_size, "rank": args.rank_dim,
+                                 "sigma": args.sigma, "delta": args.delta, "eps": args.eps, "sigma_q": args.sigma_q},
+                   "train": {"kmeans_niter": args.kmeans_niter, "points_per_centroid": args.train_pts},
+                   "build_seconds": build_s, "ndis_per_step": ndis_step,
+                   "api": "value: SearchPlane collective with device-resident queries; e2e: "
+                          "distributed_faiss.client.IndexClient.search(host ndarray) over the NCCL search plane, "
+                          "8 IndexServer shards, integer metadata"},
+        "e2e": {"value": qps_e2e, "unit": "QPS", "h2d_bytes_per_step": B * D * 4, "d2h_bytes_per_step": B * K * 12 + 8 * world,
+                "ms_per_step": ms_e2e / args.steps, "through": "IndexClient.search", "plane_equals_socket": plane_equals_socket},
+        "gpu_launches": int(launches_timed),
+        "clocks": clk,
+        "roofline": roofline,
+        "cpu_baseline": cb,
+    }
+    if sweep:
+        out["config"]["qps_by_batch"] = sweep
+        out["config"]["e2e_qps_by_batch"] = sweep_e2e
+    print(json.dumps(out), flush=True)
+    client.close()
+    plane.stop()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

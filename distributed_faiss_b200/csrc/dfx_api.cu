@@ -77,20 +77,7 @@ int dfx_create(const dfx_cfg* cfg, dfx_index** out) {
         idx->M = cfg->pq_m;
         idx->ksub = 256;
         idx->dsub = cfg->d / cfg->pq_m;
-        // experiments: DFX_SCAN_VARIANT=2 makes new indexes start on the lane-per-vector scan
-        if (const char* e = getenv("DFX_SCAN_VARIANT"))
-            if (atoi(e) == 2 || atoi(e) == 3) idx->il_variant = atoi(e);
-        if (const char* e = getenv("DFX_PREP_VARIANT"))
-            if (atoi(e) == 2) idx->prep_variant = 2;
     }
-    if (const char* e = getenv("DFX_RERANK_VARIANT"))
-        if (atoi(e) == 2) idx->rerank_variant = 2;
-    if (const char* e = getenv("DFX_IL2_RING"))
-        if (atoi(e) == 1) idx->il2_ring = true;
-    if (const char* e = getenv("DFX_ROWS_INFLIGHT"))
-        if (atoi(e) == 8) idx->rows_inflight = 8;
-    if (const char* e = getenv("DFX_FLAT_TC"))
-        if (atoi(e) == 1) idx->flat_tc = true;
     DeviceGuard g(cfg->device);
     DFX_CUDA(cudaStreamCreateWithFlags(&idx->stream, cudaStreamNonBlocking));
     *out = idx.release();
@@ -115,6 +102,7 @@ void dfx_destroy(dfx_index* idx) {
 
 int dfx_set_param(dfx_index* idx, const char* name, double value) {
     DFX_API_BEGIN
+    idx->generation++;
     std::string n(name);
     if (n == "kmeans_niter") idx->kmeans_niter = (int)value;
     else if (n == "max_points_per_centroid") idx->max_points_per_centroid = (int)value;
@@ -128,30 +116,10 @@ int dfx_set_param(dfx_index* idx, const char* name, double value) {
         if (!idx->il_enabled) dfx_pq_il_to_rm(idx, idx->stream);
         else if (idx->trained && idx->n_pending == 0 && idx->n_sorted > 0) dfx_pq_rm_to_il(idx, idx->stream);
     }
-    else if (n == "scan_ring") idx->il2_ring = value != 0;
     else if (n == "flat_tensor_cores") idx->flat_tc = value != 0;
     else if (n == "rows_inflight") {
-        DFX_REQUIRE(value == 4 || value == 8, "rows_inflight must be 4 or 8");
+        DFX_REQUIRE(value == 0 || value == 4 || value == 8, "rows_inflight must be 0 (by row size), 4 or 8");
         idx->rows_inflight = (int)value;
-    }
-    else if (n == "rerank_variant") {
-        DFX_REQUIRE(value == 1 || value == 2, "rerank_variant must be 1 or 2");
-        idx->rerank_variant = (int)value;
-    }
-    else if (n == "prep_variant") {
-        DFX_REQUIRE(value == 1 || value == 2, "prep_variant must be 1 or 2");
-        idx->prep_variant = (int)value;
-    }
-    else if (n == "scan_variant") {
-        // 1 = scan_pq_il_kernel (8 lanes per vector), 2 = scan_pq_il2_kernel (lane per vector,
-        // wide table), 3 = scan_pq_il_split_kernel (1 on coalesced halves); changes the block
-        // layout, so resident blocks are converted
-        DFX_REQUIRE(value == 1 || value == 2 || value == 3, "scan_variant must be 1, 2 or 3");
-        std::lock_guard<std::mutex> lk(idx->mu);
-        DeviceGuard g(idx->cfg.device);
-        idx->join_dev();
-        idx->il_variant = (int)value;
-        if (idx->il && idx->il_layout != idx->il_variant) dfx_pq_rm_to_il(idx, idx->stream);
     }
     else throw DfxError{"unknown parameter " + n};
     DFX_API_END
@@ -159,6 +127,7 @@ int dfx_set_param(dfx_index* idx, const char* name, double value) {
 
 int dfx_train_dev(dfx_index* idx, int64_t n, const float* d_x, void* stream) {
     DFX_API_BEGIN
+    idx->generation++;
     std::lock_guard<std::mutex> lk(idx->mu);
     DeviceGuard g(idx->cfg.device);
     idx->join_dev_if_other((cudaStream_t)stream);
@@ -168,6 +137,7 @@ int dfx_train_dev(dfx_index* idx, int64_t n, const float* d_x, void* stream) {
 }
 int dfx_add_dev(dfx_index* idx, int64_t n, const float* d_x, void* stream) {
     DFX_API_BEGIN
+    idx->generation++;
     std::lock_guard<std::mutex> lk(idx->mu);
     DeviceGuard g(idx->cfg.device);
     idx->join_dev_if_other((cudaStream_t)stream);
@@ -177,6 +147,7 @@ int dfx_add_dev(dfx_index* idx, int64_t n, const float* d_x, void* stream) {
 }
 int dfx_train(dfx_index* idx, int64_t n, const float* x) {
     DFX_API_BEGIN
+    idx->generation++;
     std::lock_guard<std::mutex> lk(idx->mu);
     DeviceGuard g(idx->cfg.device);
     idx->join_dev();
@@ -189,6 +160,7 @@ int dfx_train(dfx_index* idx, int64_t n, const float* x) {
 }
 int dfx_add(dfx_index* idx, int64_t n, const float* x) {
     DFX_API_BEGIN
+    idx->generation++;
     std::lock_guard<std::mutex> lk(idx->mu);
     DeviceGuard g(idx->cfg.device);
     idx->join_dev();
@@ -211,6 +183,7 @@ int dfx_reserve(dfx_index* idx, int64_t n_total) {
 }
 int dfx_finalize(dfx_index* idx, void* stream) {
     DFX_API_BEGIN
+    idx->generation++;
     std::lock_guard<std::mutex> lk(idx->mu);
     DeviceGuard g(idx->cfg.device);
     idx->join_dev();
@@ -279,11 +252,13 @@ int dfx_reconstruct_dev(dfx_index* idx, int64_t n, const int64_t* d_ids, int64_t
 
 int dfx_set_nprobe(dfx_index* idx, int64_t nprobe) {
     DFX_API_BEGIN
+    idx->generation++;
     DFX_REQUIRE(nprobe >= 1, "nprobe must be >= 1");
     idx->nprobe = nprobe;
     DFX_API_END
 }
 int64_t dfx_get_nprobe(const dfx_index* idx) { return idx->nprobe; }
+int64_t dfx_generation(const dfx_index* idx) { return (int64_t)idx->generation.load(); }
 int64_t dfx_ntotal(const dfx_index* idx) { return idx->ntotal(); }
 int64_t dfx_nlist(const dfx_index* idx) { return idx->cfg.kind == DFX_FLAT ? 0 : idx->cfg.nlist; }
 int dfx_is_trained(const dfx_index* idx) { return (idx->trained || idx->cfg.kind == DFX_FLAT) ? 1 : 0; }
@@ -449,6 +424,7 @@ int dfx_get_array(dfx_index* idx, const char* name, void* out, int64_t max_bytes
 
 int dfx_set_array(dfx_index* idx, const char* name, const void* in, int64_t nbytes) {
     DFX_API_BEGIN
+    idx->generation++;
     std::lock_guard<std::mutex> lk(idx->mu);
     DeviceGuard g(idx->cfg.device);
     idx->join_dev();
@@ -511,6 +487,7 @@ int dfx_set_array(dfx_index* idx, const char* name, const void* in, int64_t nbyt
 
 int dfx_import_done(dfx_index* idx) {
     DFX_API_BEGIN
+    idx->generation++;
     std::lock_guard<std::mutex> lk(idx->mu);
     DeviceGuard g(idx->cfg.device);
     idx->join_dev();

@@ -583,7 +583,7 @@ void dfx_reconstruct_impl(dfx_index* idx, int64_t n, const int64_t* d_ids, float
     if (n <= 0) return;
     if (idx->n_pending > 0) dfx_finalize_impl(idx, st);
     const int64_t nt = idx->n_sorted;
-    const int il = idx->il ? idx->il_layout : 0;  // 0 = row-major, else the block layout
+    const int il = idx->il ? 2 : 0;  // 0 = row-major, else the block layout
     if (idx->is_ivf() && !idx->inv_valid) {
         idx->inv.reserve((size_t)std::max<int64_t>(nt, 1) * 4);
         const int64_t npos = il ? idx->nblk * 32 : nt;

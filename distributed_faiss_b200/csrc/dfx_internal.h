@@ -2,6 +2,7 @@
 #pragma once
 #include "dfx_common.cuh"
 #include <vector>
+#include <atomic>
 #include <mutex>
 #include <memory>
 #include <algorithm>
@@ -35,30 +36,21 @@ struct dfx_index {
     int max_points_per_centroid = 256;  // faiss Clustering default
     uint64_t train_seed = 1234;       // faiss Clustering default seed
 
-    // IVF-PQ, M == 32: interleaved block layout for the lane-per-subquantizer scan
-    // (dfx_scan_il.cu).  While `il` is set the row-major payload/tvals/ids are released.
+    // IVF-PQ, M == 32: block-interleaved storage for the lane-per-vector scan (dfx_scan_il2.cu,
+    // layout dfx_il2_byte).  While `il` is set the row-major payload/tvals/ids are released.
     bool il = false, il_enabled = true;
     DevBuf il_codes, il_tvals, il_ids, blk_off;
     int64_t nblk = 0;
-    // which block layout / scan kernel: 1 = dfx_il_byte + scan_pq_il_kernel (default),
-    // 2 = dfx_il2_byte + scan_pq_il2_kernel (dfx_scan_il2.cu; dfx_set_param "scan_variant"),
-    // 3 = dfx_il3_byte + scan_pq_il_split_kernel (the default kernel on coalesced halves)
-    // K3 variant (dfx_set_param "prep_variant"): 2 = pq_prep2_kernel on the transposed codebook
-    int prep_variant = 1;
-    DevBuf codebooksT;  // [ksub][M][dsub], built on demand
+    DevBuf codebooksT;  // [ksub][M][dsub]: the order the fused table build reads (dfx_scan_il2.cu)
     bool cbT_valid = false;
-    int il_variant = 1;  // requested
-    int il_layout = 0;   // layout the il_* arrays currently hold (valid while `il`)
 
     // tensor-core coarse quantizer (dfx_tc.cu): bf16 hi/lo planes and screening workspace
     DevBuf tc_cent, tc_cent_tmp, tc_q, tc_gmin, tc_gmin2, tc_gargc, tc_groups, tc_cand, tc_qn, tc_amb;
     float tc_cmax2 = 0.f;
     bool tc_ready = false;
     bool tc_enabled = true;
-    int rerank_variant = 1;  // 2 = rerank2_kernel (warp per query; dfx_set_param "rerank_variant")
-    bool il2_ring = false;      // scan 2: feed the code blocks through shared-memory rings (dfx_set_param "scan_ring")
-    int rows_inflight = 4;      // vectors in flight per warp of scan_rows_kernel (8: experimental)
-    bool flat_tc = false;       // FLAT: search through the tensor-core screening (dfx_tc_flat_candidates)
+    int rows_inflight = 0;      // vectors in flight per warp of scan_rows_kernel: 0 = by row size, else 4 / 8
+    bool flat_tc = true;        // FLAT: search through the tensor-core screening (dfx_tc_flat_candidates)
     int64_t tc_flat_rows = -1;  // rows covered by the bf16 planes of a FLAT index (-1: none)
 
     // scan-kernel profiling (dfx_profile_enable)
@@ -69,6 +61,10 @@ struct dfx_index {
     // last-search bookkeeping
     int64_t last_nq = 0, last_nprobe = 0;
     bool last_keys_valid = false;
+
+    // bumped by every call that can change what a search launches (train / add / finalize /
+    // import / set_param / set_nprobe): CUDA-graph replays of a search are keyed on it
+    std::atomic<long long> generation{0};
 
     cudaStream_t stream = nullptr;  // used by the host-pointer entry points
     // stream of the most recent *_dev call; host-pointer entry points (which run on `stream`,
@@ -132,18 +128,8 @@ void dfx_stats_impl(dfx_index* idx, int64_t* ndis, cudaStream_t st);
 void dfx_launch_select_comp(const uint64_t* comp, int64_t nrows, int n, int64_t ld, int k, int32_t* keys,
                             cudaStream_t st);
 
-// Interleaved IVF-PQ block (M == 32): 32 vectors x 32 codes = 1 KB.  Vector v = 8u + w of the
-// block (u = group 0..3, w = 0..7) and subquantizer m = i + 8j (i = 0..7, j = 0..3) live at
-//   byte  lane*32 + r*4 + t   with lane = 8u + i,  r = w ^ i,  t = (j - u) & 3.
-// Lane (u,i) of the scanning warp owns subquantizers {i, i+8, i+16, i+24} of the 8 vectors of
-// group u: row r (one 32-bit word) holds their 4 codes in the order the lane looks them up
-// (j = (t + u) & 3, which makes the 32 simultaneous table reads hit 32 different banks).
-__host__ __device__ __forceinline__ int dfx_il_byte(int v, int m) {
-    const int u = v >> 3, w = v & 7, i = m & 7, j = m >> 3;
-    return (8 * u + i) * 32 + (w ^ i) * 4 + ((j - u) & 3);
-}
-
-// Layout 2 (dfx_scan_il2.cu): one lane per vector.  Lane v of the scanning warp owns vector v of
+// Interleaved IVF-PQ block (M == 32): 32 vectors x 32 codes = 1 KB, one lane per vector.
+// Lane v of the scanning warp owns vector v of
 // the block and walks its 32 subquantizers in the rotated order m = (t + v) & 31, t = 0..31, so
 // that at every step the 32 lanes read 32 different table columns (bank == column).  Byte t of
 // the lane's 32 code bytes therefore holds the code of subquantizer (t + v) & 31; the two 16-byte
@@ -153,24 +139,18 @@ __host__ __device__ __forceinline__ int dfx_il2_byte(int v, int m) {
     const int t = (m - v) & 31;
     return (t >> 4) * 512 + v * 16 + (t & 15);
 }
-// Layout 3: the words of layout 1 with each lane's two 16-byte halves stored 512 bytes apart.
-__host__ __device__ __forceinline__ int dfx_il3_byte(int v, int m) {
-    const int b = dfx_il_byte(v, m), lane = b >> 5, r = (b >> 2) & 7, t = b & 3;
-    return (r >> 2) * 512 + lane * 16 + (r & 3) * 4 + t;
-}
-__host__ __device__ __forceinline__ int dfx_il_byte_of(int layout, int v, int m) {
-    return layout == 2 ? dfx_il2_byte(v, m) : layout == 3 ? dfx_il3_byte(v, m) : dfx_il_byte(v, m);
-}
+// (the `layout` argument of the C-ABI probe dfx_debug_il_byte is kept for compatibility; there is
+// one block layout)
+__host__ __device__ __forceinline__ int dfx_il_byte_of(int /*layout*/, int v, int m) { return dfx_il2_byte(v, m); }
 
 // ---- dfx_scan_il.cu
 bool dfx_il_wanted(const dfx_index* idx);
 void dfx_pq_rm_to_il(dfx_index* idx, cudaStream_t st);
 void dfx_pq_il_to_rm(dfx_index* idx, cudaStream_t st);
-void dfx_launch_scan_pq_il(dfx_index* idx, int64_t qc, const int32_t* keys, int nprobe, int G, int ngroups,
-                           int k, int cap, uint64_t* part, cudaStream_t st);  // layout 1 or 3
-// ---- dfx_scan_il2.cu  (lutW: [nq][256][64] wide table, see pq_prep_kernel mode 2)
-void dfx_launch_scan_pq_il2(dfx_index* idx, int64_t qc, const int32_t* keys, int nprobe, int G, int ngroups,
-                            int k, int cap, uint64_t* part, cudaStream_t st);
+// ---- dfx_scan_il2.cu: K3 + K4 fused; returns true when it wrote the final (D, I) rows itself
+bool dfx_launch_scan_pq_il2(dfx_index* idx, const float* xq, int64_t qc, const int32_t* keys, int nprobe, int G,
+                            int ngroups, int k, int cap, uint64_t* part, float* outD, int64_t* outI,
+                            cudaStream_t st);
 
 // ---- dfx_tc.cu
 bool dfx_tc_supported(int d);

@@ -1,5 +1,5 @@
-// dfx_scan_il.cu -- host side of the interleaved IVF-PQ scan (K4 v2): layout conversion drivers
-// and the launcher.  Kernels: dfx_scan_il_dev.cuh.
+// dfx_scan_il.cu -- layout conversion drivers of the block-interleaved IVF-PQ storage (M == 32).
+// Kernels: dfx_scan_il_dev.cuh; the scan itself: dfx_scan_il2.cu.
 #include "dfx_scan_il_dev.cuh"
 
 bool dfx_il_wanted(const dfx_index* idx) {
@@ -9,11 +9,7 @@ bool dfx_il_wanted(const dfx_index* idx) {
 // payload/tvals/ids (row-major, list-sorted) -> il_* ; frees the row-major arrays
 void dfx_pq_rm_to_il(dfx_index* idx, cudaStream_t st) {
     if (!dfx_il_wanted(idx)) return;
-    if (idx->il) {
-        if (idx->il_layout == idx->il_variant) return;
-        dfx_pq_il_to_rm(idx, st);  // other block layout requested: go through the row-major form
-    }
-    const int layout = idx->il_variant;
+    if (idx->il) return;
     const int64_t nlist = idx->cfg.nlist;
     std::vector<int64_t> h_blk((size_t)nlist + 1);
     h_blk[0] = 0;
@@ -29,14 +25,13 @@ void dfx_pq_rm_to_il(dfx_index* idx, cudaStream_t st) {
         DFX_LAUNCH(pq_rm_to_il_kernel, (unsigned)nblk, 256, 0, st, idx->list_off.as<int64_t>(),
                    idx->blk_off.as<int64_t>(), nlist, idx->payload.as<uint8_t>(), idx->tvals.as<float>(),
                    idx->ids.as<int32_t>(), idx->il_codes.as<uint8_t>(), idx->il_tvals.as<float>(),
-                   idx->il_ids.as<int32_t>(), layout);
+                   idx->il_ids.as<int32_t>());
     DFX_CUDA(cudaStreamSynchronize(st));  // h_blk is on the stack of this call
     idx->payload.release();
     idx->tvals.release();
     idx->ids.release();
     idx->nblk = nblk;
     idx->il = true;
-    idx->il_layout = layout;
     idx->inv_valid = false;
 }
 
@@ -51,23 +46,13 @@ void dfx_pq_il_to_rm(dfx_index* idx, cudaStream_t st) {
         DFX_LAUNCH(pq_il_to_rm_kernel, (unsigned)idx->nblk, 256, 0, st, idx->list_off.as<int64_t>(),
                    idx->blk_off.as<int64_t>(), idx->cfg.nlist, idx->il_codes.as<uint8_t>(),
                    idx->il_tvals.as<float>(), idx->il_ids.as<int32_t>(), idx->payload.as<uint8_t>(),
-                   idx->tvals.as<float>(), idx->ids.as<int32_t>(), idx->il_layout);
+                   idx->tvals.as<float>(), idx->ids.as<int32_t>());
     DFX_CUDA(cudaStreamSynchronize(st));
     idx->il_codes.release();
     idx->il_tvals.release();
     idx->il_ids.release();
     idx->nblk = 0;
     idx->il = false;
-    idx->il_layout = 0;
     idx->inv_valid = false;
 }
 
-void dfx_launch_scan_pq_il(dfx_index* idx, int64_t qc, const int32_t* keys, int nprobe, int G, int ngroups, int k,
-                           int cap, uint64_t* part, cudaStream_t st) {
-    const size_t smem = (size_t)256 * 32 * 4 + (size_t)(IL_THREADS / 32) * cap * 8;
-    auto kern = (idx->il_layout == 3) ? scan_pq_il_split_kernel : scan_pq_il_kernel;
-    DFX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    DFX_LAUNCH(kern, (unsigned)(qc * ngroups), IL_THREADS, smem, st, idx->w_lut.as<float>(), idx->w_dis0.as<float>(), keys,
-               nprobe, G, ngroups, idx->blk_off.as<int64_t>(), idx->il_codes.as<uint4>(), idx->il_tvals.as<float>(),
-               idx->il_ids.as<int32_t>(), k, cap, part);
-}

@@ -1,19 +1,14 @@
 // dfx_scan_il2_dev.cuh -- device code of dfx_scan_il2.cu (also compiled by the CPU emulator, tests/emu/).
-// K4 v3: inverted-list scan of PQ codes, one lane per vector, wide table.
-// EXPERIMENTAL (dfx_set_param "scan_variant" = 2, off by default): written against the ncu
-// profile of scan_pq_il_kernel (profiles/r01_scan_pq_il_1B_v9.ncu-rep), not yet timed.
+// K3 + K4: per-query PQ table build fused into the inverted-list scan of PQ codes (M == 32), one
+// lane per vector, wide table.  The default IVF-PQ scan since round 2 (validated on B200:
+// profiles/r02_*; the 8-lanes-per-vector kernel of round 1 and the other candidates are gone).
 //
 // Replaces the inner loop of faiss IndexIVFPQ::search (reached from reference
 // distributed_faiss/index.py:257) -- `dis = dis0 + sum_m table[m][code[m]]` over every code of
 // every probed list; same canonical arithmetic as the other scan kernels (oracle pq_sum).
 //
-// What the profile of v2 said, and what changes here:
-//   * v2 is bound by the LSU data pipe (88 % of its wavefront peak): ~90 wavefronts per
-//     32-vector block, of which only 32 are the table lookups.  20 are the global loads -- each
-//     128-bit code load touched all eight 128-byte lines of the block (lanes 32 bytes apart) and
-//     moved every sector over the L2->L1 crossbar twice; ~27 are the shared-memory sorts of the
-//     per-warp candidate buffers; 7 are the butterfly shuffles.
-//   * Layout 2 (dfx_il2_byte): lane v owns vector v; the two 16-byte halves of all lanes are
+// Design (each point answers a line of the ncu profile of the round-1 kernel):
+//   * Block layout 2 (dfx_il2_byte): lane v owns vector v; the two 16-byte halves of all lanes are
 //     contiguous, so each 128-bit load of the warp is one 512-byte run (4 wavefronts).
 //   * One lane per vector needs no shuffles: lane v walks m = (t + v) & 31, t = 0..31.  The table
 //     rows are 64 floats wide (column c holds m = c & 31), so the lane reads column v + t with no
@@ -24,24 +19,39 @@
 //   * The shared-memory address of a lookup is ONE instruction: PRMT drops the code byte into
 //     byte 1 of (4 * lane), giving code * 256 + 4 * lane; the table base (uniform register) and
 //     4 * t (immediate) ride in the LDS address.  The tree is 15 packed FADD2 + 1 FADD.
-//     ~100 issued instructions per block instead of ~265.
 //   * k <= 32: the k best of a warp live in REGISTERS (lane i = i-th best, 64-bit composite);
 //     admitted candidates go to a 64-slot queue; whenever 32 are queued they are merged with a
-//     bitonic network over shuffles (42 SHFL per merge instead of a ~190-wavefront shared-memory
-//     sort), the remainder stays queued.
+//     bitonic network over shuffles, the remainder stays queued.
 //     Ids are not streamed: the queue holds positions, ids are gathered when the queue is
 //     merged (one latency per merge) or on an exact tie with the k-th best.
 //   * The block stream of a warp runs across list boundaries with two blocks in flight, so a new
 //     list does not expose a DRAM latency (a warp owns only ~7 blocks of each list).
+//   * K3 fused (round 2): the CTA builds its query's table in the prologue -- lut[m][j] =
+//     -2 * ip_seq(q_m, P[m][j]) from the transposed codebook PT[j][m][dsub] (L2-resident, 128 KB),
+//     warp w produces rows j = w, w+8, ... with lane = m, so codebook reads are 512-byte runs and
+//     the shared-memory stores are conflict-free -- and the exact |q - c|^2 of its probed lists
+//     (warp-dot).  The 64 KB per (query, shard) table no longer makes a round trip through global
+//     memory (268 MB written + 268 MB read per 4096-query launch) and the K3 launch is gone.
+//   * A CTA that owns ALL probes of its query (ngroups == 1, the large-batch regime) writes the
+//     final (D, I) rows itself; the per-query reduction launch is skipped.
 #pragma once
 #include "dfx_internal.h"
 #include "dfx_topk.cuh"
 #include "dfx_ptx.cuh"
 
-constexpr int IL2_THREADS = 256;             // default CTA size (DFX_IL2_THREADS: 384 = 2 CTAs/SM of 12 warps)
+constexpr int IL2_THREADS = 256;             // 8 warps; 3 CTAs per SM (64 KB table each)
 constexpr int IL2_LUT_BYTES = 256 * 64 * 4;  // wide table of one query
 constexpr int IL2_QCAP = 64;                 // queue slots per warp (register top-k path)
 constexpr int IL2_MAXG = 16;                 // probes per CTA (choose_group caps G at 16)
+
+// codebook in the order the fused table build of the block scan reads it: PT[j][m][dsub]
+__global__ void cb_transpose_kernel(const float* __restrict__ cb, int M, int ksub, int dsub,
+                                    float* __restrict__ cbT) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;  // over M * ksub * dsub
+    if (i >= M * ksub * dsub) return;
+    const int t = i % dsub, e = i / dsub, j = e % ksub, m = e / ksub;
+    cbT[((size_t)j * M + m) * dsub + t] = cb[i];
+}
 
 // Merge the first min(cnt, 32) entries of a warp's queue (key << 32 | position) into its
 // register-resident set and move the rest to the front of the queue; the ids of the merged
@@ -83,32 +93,24 @@ __device__ __noinline__ Il2Flushed il2_flush(uint64_t kept, uint64_t* queue, int
     return r;
 }
 
-// lutW: [nq][256][64] (wide transposed table, pq_prep_kernel mode 2)
 // REG: k <= 32, register-resident top-k;  !REG: WarpTopK buffers in shared memory (any k)
-// THREADS: 256 (3 CTAs/SM) or 384 (2 CTAs/SM): 24 warps/SM either way, 3 vs 2 tables per SM
-// RING (EXPERIMENTAL, dfx_set_param "scan_ring" = 1): the code blocks do not travel through
-// registers but through a per-warp ring of IL2_RING shared-memory slots filled by cp.async.bulk
-// (TMA engine, one mbarrier per slot): the global->SM traffic leaves the LSU pipe entirely and
-// IL2_RING blocks per warp are in flight instead of two (bytes in flight per SM are what bounds
-// a latency-limited stream).  Costs 2 x 16-byte shared loads per lane and block, and shared memory:
-// 2 CTAs/SM of 8 warps.
-constexpr int IL2_RING = 4;             // slots per warp
-constexpr int IL2_SLOT_BYTES = 1024 + 128;  // codes + t-values of one block
-template <bool REG, int THREADS = IL2_THREADS, bool RING = false>
-__global__ void __launch_bounds__(THREADS, (RING || THREADS != 256) ? 2 : 3)
-scan_pq_il2_kernel(const float* __restrict__ lutW, const float* __restrict__ dis0, const int32_t* __restrict__ keys,
-                   int nprobe, int G, int ngroups, const int64_t* __restrict__ blk_off,
-                   const uint4* __restrict__ il_codes, const float* __restrict__ il_tvals,
-                   const int32_t* __restrict__ il_ids, int k, int cap, uint64_t* __restrict__ part) {
+// Q [nq][d] queries; cbT: transposed codebook PT[j][m][dsub]; cent [nlist][d]; d = 32 * dsub.
+// outD / outI != nullptr (requires ngroups == 1): final faiss-style rows are written directly.
+template <bool REG>
+__global__ void __launch_bounds__(IL2_THREADS, 3)
+scan_pq_il2_kernel(const float* __restrict__ Q, const float* __restrict__ cbT, const float* __restrict__ cent, int d,
+                   int dsub, const int32_t* __restrict__ keys, int nprobe, int G, int ngroups,
+                   const int64_t* __restrict__ blk_off, const uint4* __restrict__ il_codes,
+                   const float* __restrict__ il_tvals, const int32_t* __restrict__ il_ids, int k, int cap,
+                   uint64_t* __restrict__ part, float* __restrict__ outD, int64_t* __restrict__ outI) {
+    constexpr int THREADS = IL2_THREADS;
     DFX_DYN_SMEM(unsigned char, smem_raw, 128);
     float* s_lut = reinterpret_cast<float*>(smem_raw);                      // [256][64]
     uint64_t* s_buf = reinterpret_cast<uint64_t*>(smem_raw + IL2_LUT_BYTES);  // queues / WarpTopK buffers
-    // RING: [LUT | queues or WarpTopK buffers | ring slots (16-byte aligned) | slot barriers]
-    __shared__ __align__(8) uint64_t s_lut_bar;
-    __shared__ __align__(8) uint64_t s_slot_bar[RING ? (THREADS / 32) * IL2_RING : 1];
     __shared__ unsigned int s_cta_key;  // CTA-wide admission bound (order-preserving key)
     __shared__ int s_lb[IL2_MAXG], s_le[IL2_MAXG];  // first / end block of each probed list
     __shared__ float s_ld0[IL2_MAXG];               // |q - c|^2 of each probed list
+    __shared__ int s_lkey[IL2_MAXG];
 
     constexpr int IL2_NW = THREADS / 32;
     const int64_t q = blockIdx.x / ngroups;
@@ -119,23 +121,63 @@ scan_pq_il2_kernel(const float* __restrict__ lutW, const float* __restrict__ dis
     // lookups become LDS [R + UR + imm]
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     const int np = min(nprobe, (g + 1) * G) - g * G;  // probes of this CTA (<= IL2_MAXG)
+    const float* qrow = Q + q * d;
 
-    if (tid == 0) {
-        s_cta_key = 0xff800000u;  // key of +inf: no bound yet
-        dfx_bulk_init(&s_lut_bar);
-        if (RING)
-            for (int i = 0; i < (THREADS / 32) * IL2_RING; i++) dfx_bulk_init(&s_slot_bar[i]);
-        dfx_bulk_init_fence();
-    }
+    if (tid == 0) s_cta_key = 0xff800000u;  // key of +inf: no bound yet
     if (tid < np) {
         const int l = keys[q * nprobe + g * G + tid];
+        s_lkey[tid] = l;
         s_lb[tid] = (l < 0) ? 0 : (int)blk_off[l];
         s_le[tid] = (l < 0) ? 0 : (int)blk_off[l + 1];
-        s_ld0[tid] = dis0[q * nprobe + g * G + tid];
+    }
+    // ---- K3, part 1: the query's table, rows j = warp, warp + 8, ...; lane = subquantizer m.
+    // seq-k order (oracle): acc = fma(q0, p0, 0), fma(q1, p1, acc), ...; entry = -2 * acc.
+    if (dsub == 4) {
+        const float4 qm = __ldg(reinterpret_cast<const float4*>(qrow) + lane);
+        const float4* pt4 = reinterpret_cast<const float4*>(cbT);
+#pragma unroll 8
+        for (int j = warp; j < 256; j += IL2_NW) {
+            const float4 pv = __ldg(pt4 + j * 32 + lane);
+            float acc = __fmaf_rn(qm.x, pv.x, 0.f);
+            acc = __fmaf_rn(qm.y, pv.y, acc);
+            acc = __fmaf_rn(qm.z, pv.z, acc);
+            acc = __fmaf_rn(qm.w, pv.w, acc);
+            const float val = -2.f * acc;
+            s_lut[j * 64 + lane] = val;
+            s_lut[j * 64 + 32 + lane] = val;
+        }
+    } else {
+        const float* qm = qrow + lane * dsub;
+        for (int j = warp; j < 256; j += IL2_NW) {
+            const float* pv = cbT + ((size_t)j * 32 + lane) * dsub;
+            float acc = 0.f;
+            for (int t = 0; t < dsub; t++) acc = __fmaf_rn(__ldg(qm + t), __ldg(pv + t), acc);
+            const float val = -2.f * acc;
+            s_lut[j * 64 + lane] = val;
+            s_lut[j * 64 + 32 + lane] = val;
+        }
+    }
+    __syncthreads();  // s_lkey visible (and the table complete)
+    // ---- K3, part 2: exact |q - c|^2 of the probed lists, canonical warp-dot order
+    for (int p = warp; p < np; p += IL2_NW) {
+        const int l = s_lkey[p];
+        float acc = 0.f;
+        if (l >= 0) {
+            const float* c = cent + (size_t)l * d;
+            for (int base = 4 * lane; base < d; base += 128) {
+                const float4 cv = __ldg(reinterpret_cast<const float4*>(c + base));
+                const float4 qv = __ldg(reinterpret_cast<const float4*>(qrow + base));
+                float df;
+                df = qv.x - cv.x; acc = __fmaf_rn(df, df, acc);
+                df = qv.y - cv.y; acc = __fmaf_rn(df, df, acc);
+                df = qv.z - cv.z; acc = __fmaf_rn(df, df, acc);
+                df = qv.w - cv.w; acc = __fmaf_rn(df, df, acc);
+            }
+        }
+        acc = dfx_warp_butterfly(acc);
+        if (lane == 0) s_ld0[p] = acc;
     }
     __syncthreads();
-    // the 64 KB table arrives by one bulk async copy (TMA engine)
-    if (tid == 0) dfx_bulk_issue(s_lut, lutW + q * (IL2_LUT_BYTES / 4), (uint32_t)IL2_LUT_BYTES, &s_lut_bar);
 
     // ---- candidate set
     WarpTopK wt;                                     // !REG
@@ -155,8 +197,6 @@ scan_pq_il2_kernel(const float* __restrict__ lutW, const float* __restrict__ dis
         thr_sec = f.thr_sec;
         cnt = f.cnt;
     };
-
-    dfx_bulk_wait(&s_lut_bar);
 
     const uint32_t lut_base = dfx_smem_addr(s_lut);
     const uint32_t cu = (uint32_t)lane * 4u;  // byte offset of column `lane`; byte 1 receives the code
@@ -244,54 +284,7 @@ scan_pq_il2_kernel(const float* __restrict__ lutW, const float* __restrict__ dis
         }                                                                    \
     } while (0)
 
-    if (RING) {
-        // ---- ring-fed stream: slot s of this warp holds block (codes 1024 B | t 128 B)
-        const size_t topk_bytes = REG ? (size_t)IL2_NW * IL2_QCAP * 8 : (size_t)IL2_NW * cap * 8;
-        unsigned char* ring = smem_raw + IL2_LUT_BYTES + ((topk_bytes + 15) / 16) * 16 +
-                              (size_t)warp * IL2_RING * IL2_SLOT_BYTES;
-        uint64_t* bars = s_slot_bar + warp * IL2_RING;
-        const uint32_t ring_addr = dfx_smem_addr(ring);
-        int spos[IL2_RING];
-        float sd0[IL2_RING];
-        auto refill = [&](int s_) {  // warp-uniform; lane 0 issues the two copies of the next block
-            if (next_block()) {
-                spos[s_] = cur_b;
-                sd0[s_] = cur_d0;
-                if (lane == 0) {
-                    dfx_bulk_expect(&bars[s_], (uint32_t)IL2_SLOT_BYTES);
-                    dfx_bulk_copy(ring + (size_t)s_ * IL2_SLOT_BYTES, il_codes + (int64_t)cur_b * 64, 1024u, &bars[s_]);
-                    dfx_bulk_copy(ring + (size_t)s_ * IL2_SLOT_BYTES + 1024, il_tvals + (int64_t)cur_b * 32, 128u,
-                                  &bars[s_]);
-                }
-            } else {
-                spos[s_] = -1;
-            }
-        };
-#pragma unroll
-        for (int s_ = 0; s_ < IL2_RING; s_++) refill(s_);
-        uint32_t parity = 0;
-        bool more = true;
-        while (more) {
-#pragma unroll
-            for (int s_ = 0; s_ < IL2_RING; s_++) {
-                if (spos[s_] < 0) {
-                    more = false;
-                    break;
-                }
-                dfx_bulk_wait_parity(&bars[s_], parity);
-                const uint32_t slot = ring_addr + (uint32_t)(s_ * IL2_SLOT_BYTES);
-                const uint4 ca = dfx_lds_v4(slot + (uint32_t)lane * 16u);
-                const uint4 cb = dfx_lds_v4(slot + 512u + (uint32_t)lane * 16u);
-                const float tv = dfx_lds_f32(slot + 1024u + (uint32_t)lane * 4u);
-                const int pos = spos[s_];
-                const float d0 = sd0[s_];
-                __syncwarp();  // every lane has read the slot: it may be refilled
-                refill(s_);
-                process(ca, cb, tv, d0, pos);
-            }
-            parity ^= 1u;
-        }
-    } else {
+    {
     uint4 a0 = {}, b0 = {}, a1 = {}, b1 = {}, a2 = {}, b2 = {};
     float t0 = 0.f, t1 = 0.f, t2 = 0.f, e0 = 0.f, e1 = 0.f, e2 = 0.f;
     int p0, p1, p2;
@@ -308,7 +301,7 @@ scan_pq_il2_kernel(const float* __restrict__ lutW, const float* __restrict__ dis
         if (p2 < 0) break;
         process(a2, b2, t2, e2, p2);
     }
-    }  // !RING
+    }
 #undef IL2_FETCH
 
     uint64_t* out = part + ((int64_t)q * ngroups + g) * k;
@@ -320,10 +313,17 @@ scan_pq_il2_kernel(const float* __restrict__ lutW, const float* __restrict__ dis
         if (warp == 0) {
 #pragma unroll 1
             for (int w2 = 1; w2 < IL2_NW; w2++) kept = dfx_warp_merge_sorted32(kept, s_buf[w2 * 32 + lane], lane);
-            if (lane < k) out[lane] = kept;
+            if (lane < k) {
+                if (outD) {  // this CTA saw every probe of the query: final faiss-style row
+                    const bool none = kept == DFX_COMP_NONE;
+                    outD[q * k + lane] = none ? FLT_MAX : dfx_key2f((uint32_t)(kept >> 32));
+                    outI[q * k + lane] = none ? -1 : (int64_t)(uint32_t)kept;
+                } else {
+                    out[lane] = kept;
+                }
+            }
         }
     } else {
         cta_merge_and_write<THREADS>(wt, s_buf, cap, k, out);
     }
 }
-

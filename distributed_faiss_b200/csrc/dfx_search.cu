@@ -616,7 +616,7 @@ void dfx_search_impl(dfx_index* idx, int64_t nq, const float* d_x, int64_t k64, 
             return;
         }
         float* qnorm_tc = nullptr;
-        if (idx->flat_tc && idx->tc_enabled) {  // experimental: screening on tensor cores + exact re-rank
+        if (idx->flat_tc && idx->tc_enabled) {  // screening on tensor cores + exact re-rank
             const int64_t ng = dfx_ceil_div(N, 128) * 4;
             const int64_t QT = std::max<int64_t>(128, ((64ll << 20) / (ng * 4)) / 128 * 128);
             bool handled = true;
@@ -720,37 +720,21 @@ void dfx_search_impl(dfx_index* idx, int64_t nq, const float* d_x, int64_t k64, 
             DFX_CUDA(cudaEventRecord(pev->first, st));
         }
 
-        if (kind == DFX_IVF_PQ) {
+        bool final_written = false;
+        if (kind == DFX_IVF_PQ && idx->il) {
+            // M == 32: table build + exact |q-c|^2 + block scan in ONE kernel; with a single probe
+            // group per query it also writes the final rows (dfx_scan_il2.cu)
+            final_written = dfx_launch_scan_pq_il2(idx, xq, qc, keys, nprobe, G, ngroups, k, cap, part, d_D + q0 * k,
+                                                   d_I + q0 * k, st);
+        } else if (kind == DFX_IVF_PQ) {
             const int M = idx->M, ksub = idx->ksub;
-            const int il = idx->il ? idx->il_layout : 0;  // 0 row-major, 1 / 2 = block layout
-            idx->w_lut.reserve((size_t)qc * M * ksub * 4 * (il == 2 ? 2 : 1));
+            idx->w_lut.reserve((size_t)qc * M * ksub * 4);
             idx->w_dis0.reserve((size_t)qc * nprobe * 4);
-            const size_t prep_smem = (size_t)((d + 3) / 4) * 16 + (il ? (size_t)M * (ksub + 1) * 4 : 0);
-            if (prep_smem > 48 * 1024)
-                DFX_CUDA(cudaFuncSetAttribute(pq_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                              (int)prep_smem));
-            if (idx->prep_variant == 2 && il && M == 32 && ksub == 256 && idx->dsub == 4) {
-                // experimental K3: tables produced in output order from the transposed codebook,
-                // 8 queries per CTA (dfx_pq_prep_dev.cuh)
-                if (!idx->cbT_valid) {
-                    idx->codebooksT.reserve((size_t)M * ksub * idx->dsub * 4);
-                    DFX_LAUNCH(cb_transpose_kernel, (unsigned)((M * ksub * idx->dsub + 255) / 256), 256, 0, st,
-                               idx->codebooks.as<float>(), M, ksub, idx->dsub, idx->codebooksT.as<float>());
-                    idx->cbT_valid = true;
-                }
-                constexpr int QB = 8;
-                DFX_LAUNCH(pq_prep2_kernel<QB>, (unsigned)((qc + QB - 1) / QB), 256, (size_t)QB * d * 4, st, xq,
-                           qc, d, idx->codebooksT.as<float>(), idx->centroids.as<float>(), keys, nprobe,
-                           idx->w_lut.as<float>(), idx->w_dis0.as<float>(), il == 2 ? 1 : 0);
-            } else
+            const size_t prep_smem = (size_t)((d + 3) / 4) * 16;
             DFX_LAUNCH(pq_prep_kernel, (unsigned)qc, 256, prep_smem, st, xq, d, M, ksub, idx->dsub,
                        idx->codebooks.as<float>(), idx->centroids.as<float>(), keys, nprobe,
-                       idx->w_lut.as<float>(), idx->w_dis0.as<float>(), il == 3 ? 1 : il);
-            if (il == 2) {
-                dfx_launch_scan_pq_il2(idx, qc, keys, nprobe, G, ngroups, k, cap, part, st);
-            } else if (il) {
-                dfx_launch_scan_pq_il(idx, qc, keys, nprobe, G, ngroups, k, cap, part, st);
-            } else {
+                       idx->w_lut.as<float>(), idx->w_dis0.as<float>());
+            {
             const size_t smem = (size_t)M * ksub * 4 + (size_t)4 * cap * 8;
 #define DFX_SCAN_PQ(MT)                                                                          \
     do {                                                                                         \
@@ -772,9 +756,13 @@ void dfx_search_impl(dfx_index* idx, int64_t nq, const float* d_x, int64_t k64, 
         } else {
             const int dq = (kind == DFX_IVF_SQ16) ? 2 * d : d;
             const size_t smem = (((size_t)dq * 4 + 15) / 16) * 16 + (size_t)4 * cap * 8;
+            // vectors in flight per warp: rows of up to 1 KB need 8 to cover the DRAM latency
+            // (B200, C2 512 B rows: 3.0 -> 4.6 TB/s), longer rows are faster with 4 (C4 1536 B rows:
+            // 4.5 vs 3.2 TB/s); profiles/r02_other_configs.json
+            const int inflight = idx->rows_inflight ? idx->rows_inflight : (idx->row_bytes() <= 1024 ? 8 : 4);
 #define DFX_SCAN_ROWS(MODE)                                                                      \
     do {                                                                                         \
-        auto kern = (idx->rows_inflight == 8) ? scan_rows_kernel<MODE, 8> : scan_rows_kernel<MODE, 4>; \
+        auto kern = (inflight == 8) ? scan_rows_kernel<MODE, 8> : scan_rows_kernel<MODE, 4>; \
         DFX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,         \
                                       (int)smem));                                               \
         DFX_LAUNCH(kern, (unsigned)(qc * ngroups), 128, smem, st, xq, d, idx->centroids.as<float>(), \
@@ -787,9 +775,11 @@ void dfx_search_impl(dfx_index* idx, int64_t nq, const float* d_x, int64_t k64, 
 #undef DFX_SCAN_ROWS
         }
         if (pev) DFX_CUDA(cudaEventRecord(pev->second, st));
-        CompLoader ldr{part, (int64_t)ngroups * k};
-        ResultWriter wr{d_D + q0 * k, d_I + q0 * k, k, smetric, 0.f, nullptr};
-        dfx_launch_select<128>(ldr, wr, qc, ngroups * k, k, st);
+        if (!final_written) {
+            CompLoader ldr{part, (int64_t)ngroups * k};
+            ResultWriter wr{d_D + q0 * k, d_I + q0 * k, k, smetric, 0.f, nullptr};
+            dfx_launch_select<128>(ldr, wr, qc, ngroups * k, k, st);
+        }
     }
     idx->last_nq = nq;
     idx->last_nprobe = nprobe;

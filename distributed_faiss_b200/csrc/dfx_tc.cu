@@ -624,9 +624,9 @@ rerank_kernel(const float* __restrict__ Q, int d, const float* __restrict__ cent
     }
 }
 
-// EXPERIMENTAL (dfx_set_param "rerank_variant" = 2, off by default; search path, nprobe <= 32,
-// G <= 64): the same decision as rerank_kernel<2>, one WARP per query instead of one 128-thread
-// CTA.  rerank_kernel<2> costs 62 us per 4096-query launch although only ~9 candidates per query
+// Search path, nprobe <= 32 and G <= 64 (the default there since round 2; measured on B200: the
+// decide stage of a 4096-query launch drops from 62 us to ~20 us): the same decision as
+// rerank_kernel<2>, one WARP per query instead of one 128-thread CTA.  rerank_kernel<2> costs 62 us per 4096-query launch although only ~9 candidates per query
 // survive the screening: one thread sums |q|^2 serially, 128 threads walk 512 candidate slots of
 // which a handful are live, then a block-wide sort.  Here: lanes own the selected groups, live
 // candidates are compacted into a per-warp list (arg-min column, or all 32 columns of a group
@@ -890,7 +890,7 @@ void dfx_tc_coarse_search(dfx_index* idx, const float* d_x, int64_t nq, int npro
                                    nullptr, nullptr, 0, st);
         }
         const int P_cand = dfx_next_pow2(G * 32 < 32 ? 32 : G * 32);
-        if (idx->rerank_variant == 2 && nprobe <= 32 && G <= 64 && d % 4 == 0) {  // experimental
+        if (nprobe <= 32 && G <= 64 && d % 4 == 0) {  // warp per query
             const size_t smem = (size_t)RR2_WARPS * ((d + 3) / 4 * 4) * 4 + (size_t)RR2_WARPS * G * 32 * 4;
             DFX_LAUNCH(rerank2_kernel, (unsigned)dfx_ceil_div(qc, RR2_WARPS), RR2_WARPS * 32, smem, st, d_x + q0 * d, d,
                        idx->centroids.as<float>(), idx->cnorm.as<float>(), nlist, idx->cfg.metric,
@@ -918,7 +918,9 @@ void dfx_tc_coarse_search(dfx_index* idx, const float* d_x, int64_t nq, int npro
     }
 }
 
-// EXPERIMENTAL (dfx_set_param "flat_tensor_cores" = 1, off by default): flat search (reference
+// Flat search on tensor cores (default for d in {64, 128}, N >= 1024, k <= 100; dfx_set_param
+// "flat_tensor_cores" = 0 selects the FFMA GEMM; measured on B200, config C1 100 k x 1 k queries:
+// 13 -> 161 TFLOP/s algorithmic, bit-exact): flat search (reference
 // index.py:94 IndexFlatIP, and IndexFlatL2 of the C-ABI) through the same machinery, with the
 // database rows in place of the centroids and k in place of nprobe.  Screening on tensor cores
 // over bf16 planes of the rows (built lazily, rebuilt after an add), the k + 8 groups with the

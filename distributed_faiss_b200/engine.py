@@ -31,7 +31,7 @@ KIND_NAMES = {KIND_FLAT: "flat", KIND_IVF_FLAT: "ivf_flat", KIND_IVF_PQ: "ivf_pq
 EXPORTED_SYMBOLS = [
     "dfx_create", "dfx_destroy", "dfx_train", "dfx_add", "dfx_train_dev", "dfx_add_dev", "dfx_set_param",
     "dfx_reserve", "dfx_finalize", "dfx_search", "dfx_search_dev", "dfx_reconstruct", "dfx_set_nprobe",
-    "dfx_get_nprobe", "dfx_ntotal", "dfx_nlist", "dfx_is_trained", "dfx_get_centroids", "dfx_merge",
+    "dfx_get_nprobe", "dfx_generation", "dfx_ntotal", "dfx_nlist", "dfx_is_trained", "dfx_get_centroids", "dfx_merge",
     "dfx_merge_dev", "dfx_merge_packed_dev", "dfx_encode_ids_dev", "dfx_filter_compact_dev",
     "dfx_reconstruct_dev", "dfx_map_ids_dev", "dfx_get_array", "dfx_set_array", "dfx_import_done",
     "dfx_last_stats", "dfx_profile_enable", "dfx_profile_read", "dfx_launch_count", "dfx_synth_init", "dfx_synth_rows_dev", "dfx_free",
@@ -66,7 +66,7 @@ def lib():
             L = C.CDLL(LIB_PATH)
             L.dfx_last_error.restype = C.c_char_p
             L.dfx_version.restype = C.c_char_p
-            for f in ("dfx_get_nprobe", "dfx_ntotal", "dfx_nlist", "dfx_launch_count"):
+            for f in ("dfx_get_nprobe", "dfx_generation", "dfx_ntotal", "dfx_nlist", "dfx_launch_count"):
                 getattr(L, f).restype = C.c_int64
             L.dfx_destroy.restype = None
             _lib = L
@@ -142,6 +142,10 @@ class GpuIndex:
     @nprobe.setter
     def nprobe(self, v):
         _check(lib().dfx_set_nprobe(self._h, C.c_int64(int(v))))
+
+    @property
+    def generation(self):
+        return int(lib().dfx_generation(self._h))
 
     @property
     def is_trained(self):

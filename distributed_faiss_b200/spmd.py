@@ -128,14 +128,15 @@ class ShardGroup:
             self._stream_max_nq = int(os.environ.get("DFX_SHARD_STREAMS_MAX_NQ", "1024"))
             n_side = int(os.environ.get("DFX_SHARD_STREAMS", "4"))
             self._streams = [torch.cuda.Stream(device=self.device) for _ in range(max(0, n_side))]
-        # latency-bound batches can be replayed from a CUDA graph captured per (nq, k, maximize)
-        # shape (single rank only; DFX_GRAPHS=1).  Graphs are dropped whenever nprobe changes; do
-        # not add to the shards while graphs are alive.
+        # latency-bound batches (a batch-1 search over 8 shards is ~50 short launches whose issue
+        # cost dominates: 0.39 -> 0.15 ms on a B200, profiles/r02_*) are replayed from a CUDA graph
+        # captured per (shape, options, shard generations); single rank only (DFX_GRAPHS=0 disables)
         self.last_error = None
         self._graphs = {}
+        self._graph_gens = None
         self._graph_max_nq = 0
         if self.device.type == "cuda" and isinstance(self.backend, CudaBackend) and self.world == 1:
-            if os.environ.get("DFX_GRAPHS") == "1":
+            if os.environ.get("DFX_GRAPHS", "1") != "0":
                 self._graph_max_nq = int(os.environ.get("DFX_GRAPHS_MAX_NQ", "256"))
 
     @property
@@ -161,13 +162,32 @@ class ShardGroup:
         Returns (D [nq,k] float32 ascending -- negated scores when `maximize`, as the reference
         returns them for metric "dot" --, I [nq,k] int64 caller ids, -1 = no result), on device,
         identical on every rank."""
-        if self._graph_max_nq and x_t.is_cuda and x_t.shape[0] <= self._graph_max_nq:
-            return self._search_graphed(x_t, k, maximize)
         out = self.search_ex(x_t, k, maximize, src)
         return out.D, out.I
 
-    def _search_graphed(self, x_t, k, maximize):
-        key = (tuple(x_t.shape), int(k), bool(maximize))
+    def search_ex(self, x_t: torch.Tensor, k: int, maximize: bool = False, src: Optional[int] = 0, *,
+                  ids: str = "table", shard_ok: Optional[Sequence[bool]] = None, status: int = 0,
+                  cols: Optional[Sequence] = None, drop_codes: Optional[Sequence[int]] = None,
+                  k_out: Optional[int] = None, return_embeddings: bool = False,
+                  meta_tables: Optional[Sequence] = None, dst: int = 0) -> SearchOut:
+        """The collective with every option of the client API (see _search_ex_eager).  Small
+        batches of the plain form are replayed from a captured CUDA graph."""
+        if (self._graph_max_nq and x_t.is_cuda and x_t.shape[0] <= self._graph_max_nq and cols is None
+                and not return_embeddings and (shard_ok is None or all(shard_ok))):
+            out = self._search_ex_graphed(x_t, k, maximize, ids, status)
+            if out is not None:
+                return out
+        return self._search_ex_eager(x_t, k, maximize, src, ids=ids, shard_ok=shard_ok, status=status, cols=cols,
+                                     drop_codes=drop_codes, k_out=k_out, return_embeddings=return_embeddings,
+                                     meta_tables=meta_tables, dst=dst)
+
+    def _search_ex_graphed(self, x_t, k, maximize, ids, status):
+        gens = tuple(s.generation for s in self.shards)
+        if gens != self._graph_gens:      # a shard changed (add / nprobe / ...): every capture is stale
+            self._graphs.clear()
+            self._graph_gens = gens
+        key = (tuple(x_t.shape), int(k), bool(maximize), ids, int(status),
+               tuple(0 if t is None else t.data_ptr() for t in self.id_tables))
         ent = self._graphs.get(key)
         if ent is None:
             static_x = x_t.clone()
@@ -176,13 +196,13 @@ class ShardGroup:
             side.wait_stream(cur)
             with torch.cuda.stream(side):  # two eager passes: workspaces reach their final size
                 for _ in range(2):
-                    self.search_ex(static_x, k, maximize, None)
+                    self._search_ex_eager(static_x, k, maximize, None, ids=ids, status=status)
             cur.wait_stream(side)
+            torch.cuda.synchronize(x_t.device)
             graph = torch.cuda.CUDAGraph()
             try:
                 with torch.cuda.graph(graph):
-                    o = self.search_ex(static_x, k, maximize, None)
-                    out = (o.D, o.I)
+                    out = self._search_ex_eager(static_x, k, maximize, None, ids=ids, status=status)
             except RuntimeError as e:  # something in the path is not capturable: stay eager
                 import logging
 
@@ -190,20 +210,19 @@ class ShardGroup:
                 self._graph_max_nq = 0
                 self._graphs.clear()
                 torch.cuda.synchronize(x_t.device)
-                o = self.search_ex(x_t, k, maximize, None)
-                return o.D, o.I
+                return None
             ent = (graph, static_x, out)
             self._graphs[key] = ent
         graph, static_x, out = ent
         static_x.copy_(x_t)
         graph.replay()
-        return out[0].clone(), out[1].clone()
+        return SearchOut(out.D.clone(), out.I.clone(), status=out.status.clone())
 
-    def search_ex(self, x_t: torch.Tensor, k: int, maximize: bool = False, src: Optional[int] = 0, *,
-                  ids: str = "table", shard_ok: Optional[Sequence[bool]] = None, status: int = 0,
-                  cols: Optional[Sequence] = None, drop_codes: Optional[Sequence[int]] = None,
-                  k_out: Optional[int] = None, return_embeddings: bool = False,
-                  meta_tables: Optional[Sequence] = None, dst: int = 0) -> SearchOut:
+    def _search_ex_eager(self, x_t: torch.Tensor, k: int, maximize: bool = False, src: Optional[int] = 0, *,
+                         ids: str = "table", shard_ok: Optional[Sequence[bool]] = None, status: int = 0,
+                         cols: Optional[Sequence] = None, drop_codes: Optional[Sequence[int]] = None,
+                         k_out: Optional[int] = None, return_embeddings: bool = False,
+                         meta_tables: Optional[Sequence] = None, dst: int = 0) -> SearchOut:
         """The collective with every option of the client API.
 
         ids          "table": I = id_tables[j][local id] (or the local id when the table is None);

@@ -113,6 +113,9 @@ int dfx_reconstruct_dev(dfx_index *idx, int64_t n, const int64_t *d_ids, int64_t
 int dfx_set_nprobe(dfx_index *idx, int64_t nprobe);
 int64_t dfx_get_nprobe(const dfx_index *idx);
 int64_t dfx_ntotal(const dfx_index *idx);
+/* changes whenever a call may have changed what a search launches (train / add / finalize /
+ * import / set_param / set_nprobe); callers that replay captured CUDA graphs key them on it */
+int64_t dfx_generation(const dfx_index *idx);
 int64_t dfx_nlist(const dfx_index *idx);
 int dfx_is_trained(const dfx_index *idx);
 int dfx_get_centroids(dfx_index *idx, float *out /* [nlist, d] host */);

@@ -38,8 +38,7 @@ while time.time() - t0 < budget:
             o.train_niter = 2
             o.train(xt)
             if kind == "ivf_pq" and M == 32 and rs.rand() < 0.5:
-                g.set_param("scan_variant", int(rs.choice([2, 3]))); g.set_param("prep_variant", int(rs.choice([1, 2])))
-                g.set_param("scan_ring", int(rs.randint(0, 2)))
+                g.set_param("interleaved", int(rs.randint(0, 2)))
             if kind in ("ivf_flat", "ivf_sq") and rs.rand() < 0.5: g.set_param("rows_inflight", 8)
         # ship the trained (empty) state, then add on both sides in the same chunks
         if kind != "flat":

@@ -2,7 +2,7 @@
 (distributed_faiss_b200/csrc/*.cu, host drivers included) with g++ on top of the fiber SIMT
 runtime, and a subset of the `gpu` parity tests is run against that build in a subprocess
 (DFX_EMU_LIB, see tests/conftest.py).  This is how host-side changes and the experimental kernel
-variants (scan_variant 2 / 3, prep_variant 2) are checked in a container without a GPU: same
+kernels are checked in a container without a GPU: same
 sources, same tests, same oracle; only the PTX primitives (dfx_ptx.cuh) and the tcgen05 screening
 kernel (its result is restated in C++; everything around it is the product code) are not what runs
 on hardware.
@@ -31,8 +31,9 @@ SUBSET = [
     "tests/test_gpu_parity.py::test_ivf_edge_cases",
     "tests/test_gpu_parity.py::test_merge_reference_golden",
     "tests/test_gpu_parity.py::test_merge_matches_oracle[8-64-10]",
+    "tests/test_gpu_parity.py::test_exchange_kernels_match_numpy",    # packed merge, encode, filter, owner decode
     "tests/test_gpu_parity.py::test_interleaved_and_row_major_pq_layouts_agree",
-    "tests/test_gpu_parity.py::test_scan_variant_2_matches_oracle",   # scan_variant 1/2/3, prep_variant 2
+    "tests/test_gpu_parity.py::test_block_scan_matches_oracle",   # K3 + K4 fused block scan
     "tests/test_gpu_api.py::test_sharded_equals_unsharded_exactly",   # servers + client over the C-ABI
     "tests/test_gpu_api.py::test_result_aggregation_on_device",
     # coarse quantizer through the tensor-core path: screening restated in C++ (dfx_tc.cu, DFX_EMU),

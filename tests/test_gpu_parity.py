@@ -346,11 +346,6 @@ def test_tensor_core_coarse_quantizer_matches_oracle(kind, metric, d, M):
         g.set_param("tensor_cores", 0)
         Df, If = g.search(xq, 10)
         _assert_same(Df, If, Do, Io, f"FFMA coarse {kind} nprobe={nprobe}")
-        if __import__("os").environ.get("DFX_EXPERIMENTAL") == "1":   # warp-per-query re-rank (not yet run on hardware)
-            g.set_param("tensor_cores", 1)
-            g.set_param("rerank_variant", 2)
-            _assert_same(*g.search(xq, 10), Do, Io, f"TC coarse, rerank variant 2, {kind} nprobe={nprobe}")
-            g.set_param("rerank_variant", 1)
     g.set_param("tensor_cores", 1)
     D1, I1 = g.search(xq[3:4], 10)  # single query: a 128-row tile with one valid row
     g.nprobe = 64
@@ -382,8 +377,8 @@ def test_tensor_core_assign_matches_oracle():
 
 
 def test_interleaved_and_row_major_pq_layouts_agree():
-    """IVF-PQ, M=32: the interleaved lane-per-subquantizer scan (default) and the row-major
-    lane-per-vector scan return the same bits as the oracle; export/import/reconstruct work in
+    """IVF-PQ, M=32: the block scan with its fused table build (default) and the row-major scan
+    (table from pq_prep_kernel) return the same bits as the oracle; export/import/reconstruct work in
     both layouts and across incremental adds."""
     from oracle import oracle as O
 
@@ -421,12 +416,12 @@ def test_interleaved_and_row_major_pq_layouts_agree():
     _assert_same(*g2.search(xq, 10), *o.search(xq, 10), "imported, interleaved")
 
 
-@pytest.mark.skipif(__import__("os").environ.get("DFX_EXPERIMENTAL") != "1",
-                    reason="scan_variant=2 has not been validated on hardware yet; run with DFX_EXPERIMENTAL=1")
-def test_scan_variant_2_matches_oracle():
-    """IVF-PQ, M=32, experimental lane-per-vector scan (dfx_scan_il2.cu): block layout 2, wide
-    table, register top-k (k <= 32) and the shared-memory fallback (k > 32) return the oracle's
-    bits; layout changes in both directions, incremental adds, export/import and reconstruct."""
+def test_block_scan_matches_oracle():
+    """IVF-PQ, M=32, the lane-per-vector block scan with the table build fused into its prologue
+    (dfx_scan_il2.cu): register top-k (k <= 32) and the shared-memory path (k > 32), one CTA per
+    query writing final rows (large batch) and several CTAs per query (small batch) all return the
+    oracle's bits, including id ties; incremental adds, export/import and reconstruct; d = 64 and
+    d = 256 take the generic-dsub table build."""
     from oracle import oracle as O
 
     E = _engine()
@@ -437,13 +432,12 @@ def test_scan_variant_2_matches_oracle():
     xq = xb[:37] + 0.01 * rs.randn(37, d).astype(np.float32)
     xq[:5] = xb[:5]
     g = E.GpuIndex(E.KIND_IVF_PQ, d, L2, nlist=nlist, pq_m=M)
-    g.set_param("scan_variant", 2)
     if EMU:
         g.set_param("kmeans_niter", 3)
     g.train(xb[:_sz(8000, 1500)])
     g.add(xb[:_sz(10_000, n // 3)]); g.nprobe = 6
-    g.search(xq, 10)                                 # builds layout 2
-    g.add(xb[_sz(10_000, n // 3):])                  # incremental add on top of it
+    g.search(xq, 10)                                 # builds the blocks
+    g.add(xb[_sz(10_000, n // 3):])                  # incremental add on top of them
     o = O.OracleIVFPQ(d, nlist, M, 8, coarse_metric=L2)
     o.set_state(g.get_state())
     assert o.ntotal == n
@@ -451,43 +445,33 @@ def test_scan_variant_2_matches_oracle():
     for nprobe, k in ((6, 10), (nlist, 32), (1, 1), (_sz(17, 7), 7), (nlist, 100), (8, 300)):
         g.nprobe = nprobe; o.nprobe = nprobe
         Do, Io = o.search(xq, k)
-        g.set_param("scan_variant", 2)
-        _assert_same(*g.search(xq, k), Do, Io, f"variant 2 nprobe={nprobe} k={k}")
-        g.set_param("scan_ring", 1)                   # same kernel fed through cp.async.bulk rings
-        _assert_same(*g.search(xq, k), Do, Io, f"variant 2 + ring nprobe={nprobe} k={k}")
-        g.set_param("scan_ring", 0)
+        _assert_same(*g.search(xq, k), Do, Io, f"block scan nprobe={nprobe} k={k}")
         R2 = g.reconstruct_rows(ids)
-        g.set_param("scan_variant", 3)                # the shipping kernel on coalesced halves
-        _assert_same(*g.search(xq, k), Do, Io, f"variant 3 nprobe={nprobe} k={k}")
-        R3 = g.reconstruct_rows(ids)
-        g.set_param("scan_variant", 1)
-        _assert_same(*g.search(xq, k), Do, Io, f"variant 1 nprobe={nprobe} k={k}")
-        R1 = g.reconstruct_rows(ids)
-        assert np.array_equal(R1[[0, 1, 2, 4]], R2[[0, 1, 2, 4]]) and np.isnan(R2[3]).all()
-        assert np.array_equal(R1[[0, 1, 2, 4]], R3[[0, 1, 2, 4]])
-    g.set_param("scan_variant", 2)
-    for nq in (1, 3, 200):                           # one list per CTA at small batches
-        q = np.ascontiguousarray(np.tile(xq, (6, 1))[:nq])
+        assert np.isnan(R2[3]).all()
+        assert np.allclose(R2[[0, 1, 2, 4]], o.reconstruct_rows(ids)[[0, 1, 2, 4]], rtol=0, atol=1e-6)
+    for nq in (1, 3, 200, _sz(1500, 200)):           # one list per CTA ... one CTA per query
+        q = np.ascontiguousarray(np.tile(xq, (_sz(41, 6), 1))[:nq])
         g.nprobe = 9; o.nprobe = 9
-        _assert_same(*g.search(q, 10), *o.search(q, 10), f"variant 2 nq={nq}")
+        _assert_same(*g.search(q, 10), *o.search(q, 10), f"block scan nq={nq}")
     g2 = E.GpuIndex(E.KIND_IVF_PQ, d, L2, nlist=nlist, pq_m=M)
-    g2.set_param("scan_variant", 2)
     g2.set_state(o.get_state())
     g2.nprobe = 6; o.nprobe = 6
-    _assert_same(*g2.search(xq, 10), *o.search(xq, 10), "imported, variant 2")
-    # experimental K3 (prep_variant 2: transposed codebook, 8 queries per CTA) under both scans
-    g2.set_param("prep_variant", 2)
-    for variant in (2, 1):
-        g2.set_param("scan_variant", variant)
-        for nq in (1, 13, 37):
-            _assert_same(*g2.search(xq[:nq], 10), *o.search(xq[:nq], 10), f"prep 2, scan {variant}, nq={nq}")
+    _assert_same(*g2.search(xq, 10), *o.search(xq, 10), "imported")
+    for d2 in (64, 256):                             # dsub = 2 / 8: generic table build
+        xb2 = clustered(rs, _sz(6000, 1500), d2, ncl=40)
+        g3 = E.GpuIndex(E.KIND_IVF_PQ, d2, L2, nlist=8, pq_m=32)
+        g3.set_param("kmeans_niter", 3)
+        g3.train(xb2[:_sz(3000, 1000)]); g3.add(xb2); g3.nprobe = 4
+        o3 = O.OracleIVFPQ(d2, 8, 32, 8, coarse_metric=L2)
+        o3.set_state(g3.get_state()); o3.nprobe = 4
+        for nq in (2, _sz(700, 90)):
+            q = np.ascontiguousarray(np.tile(xb2[:50], (_sz(14, 2), 1))[:nq])
+            _assert_same(*g3.search(q, 10), *o3.search(q, 10), f"block scan d={d2} nq={nq}")
 
 
-@pytest.mark.skipif(__import__("os").environ.get("DFX_EXPERIMENTAL") != "1",
-                    reason="flat search through the tensor-core screening has not been validated on hardware yet")
 @pytest.mark.parametrize("metric", [IP, L2])
 def test_flat_tensor_core_path_matches_oracle(metric):
-    """flat_tensor_cores=1: screening on tensor cores + exact canonical re-rank returns the bits of
+    """flat_tensor_cores=1 (the default): screening on tensor cores + exact canonical re-rank returns the bits of
     the plain GEMM path and of the oracle (ties, k up to 100, rows added after the first search)"""
     from oracle import oracle as O
 
@@ -510,3 +494,118 @@ def test_flat_tensor_core_path_matches_oracle(metric):
     g.set_param("flat_tensor_cores", 1)
     _assert_same(*g.search(xq, 10), *o.search(xq, 10), "flat TC after add")
     _assert_same(*g.search(xq[:1], 5), *o.search(xq[:1], 5), "flat TC nq=1")
+
+
+# ------------------------------------------------------------------ exchange kernels of the data plane
+class _Dev:
+    """a device buffer for the raw `*_dev` entry points: a CUDA tensor on a GPU, the numpy array
+    itself on the emulated library (its 'device memory' is host memory)"""
+
+    def __init__(self, arr):
+        self.shape, self.dtype = arr.shape, arr.dtype
+        if EMU:
+            self.a = np.ascontiguousarray(arr).copy()
+            self.ptr = self.a.ctypes.data
+        else:
+            import torch
+
+            self.t = torch.from_numpy(np.ascontiguousarray(arr)).cuda()
+            self.ptr = self.t.data_ptr()
+
+    def get(self):
+        if EMU:
+            return self.a
+        import torch
+
+        torch.cuda.synchronize()
+        return self.t.cpu().numpy()
+
+
+def test_exchange_kernels_match_numpy():
+    """dfx_merge_packed_dev == dfx_merge over the same blocks (the layout ONE all-gather delivers);
+    dfx_encode_ids_dev / dfx_filter_compact_dev == the reference's post-filter loop
+    (client.py:229-250); dfx_reconstruct_dev with a shard tag decodes exactly the owned winners"""
+    import ctypes as C
+    from oracle import oracle as O
+
+    E = _engine()
+    L = E.lib()
+    rs = np.random.RandomState(77)
+    R, S_loc, nq, k = 3, 2, 9, 5
+    n = S_loc * nq * k
+    D = np.sort(rs.rand(R * S_loc, nq, k).astype(np.float32), axis=2)
+    D[1, :, 3:] = np.finfo(np.float32).max                 # a shard with fewer than k hits
+    D[2, 4, :] = D[0, 4, :]                                  # exact ties across shards: earlier shard wins
+    I = rs.randint(0, 1 << 40, size=(R * S_loc, nq, k)).astype(np.int64)
+    I[1, :, 3:] = -1
+    off_I = (4 * n + 7) & ~7
+    stride = off_I + 8 * n + 8
+    packed = np.zeros(R * stride, dtype=np.uint8)
+    for r in range(R):
+        blk = packed[r * stride:(r + 1) * stride]
+        blk[:4 * n] = D[r * S_loc:(r + 1) * S_loc].reshape(-1).view(np.uint8)
+        blk[off_I:off_I + 8 * n] = I[r * S_loc:(r + 1) * S_loc].reshape(-1).view(np.uint8)
+    for negate in (0, 1):
+        Dm = -D if negate else D
+        Dm = np.where(np.abs(D) >= np.finfo(np.float32).max, D, Dm).astype(np.float32)
+        Dref, Pref = O.merge(Dm, np.arange(I.size, dtype=np.int64).reshape(I.shape))
+        Iref = np.where(Pref >= 0, I.reshape(-1)[np.maximum(Pref, 0)], -1)
+        src = np.where(np.abs(D) >= np.finfo(np.float32).max, np.float32(-3.4e38) if negate else D, D).astype(np.float32)
+        for r in range(R):
+            packed[r * stride:r * stride + 4 * n] = src[r * S_loc:(r + 1) * S_loc].reshape(-1).view(np.uint8)
+        dp, oD, oI = _Dev(packed), _Dev(np.zeros((nq, k), np.float32)), _Dev(np.zeros((nq, k), np.int64))
+        rc = L.dfx_merge_packed_dev(C.c_int64(R), C.c_int64(S_loc), C.c_int64(nq), C.c_int64(k), C.c_void_p(dp.ptr),
+                                    C.c_int64(stride), C.c_int64(off_I), C.c_int(negate), C.c_void_p(oD.ptr),
+                                    C.c_void_p(oI.ptr), None)
+        assert rc == 0, L.dfx_last_error()
+        Dh, Ih = E.merge(src, I, negate=bool(negate))       # the unpacked entry point on the same blocks
+        assert np.array_equal(oD.get(), Dh) and np.array_equal(oI.get(), Ih)
+        if not negate:
+            assert np.array_equal(Dh, Dref) and np.array_equal(Ih, Iref)
+
+    # encode + filter: flags ride in bit 62, compaction keeps the order and stops at k_out
+    ncol = 500
+    col = rs.randint(0, 4, size=ncol).astype(np.int32)
+    col[rs.rand(ncol) < 0.1] = -2
+    kin, kout = 41, 7
+    ids = rs.randint(0, ncol, size=(nq, kin)).astype(np.int64)
+    ids[:, 30:] = np.where(rs.rand(nq, kin - 30) < 0.5, -1, ids[:, 30:])
+    ids[3, :] = np.nonzero(col == 2)[0][0]                  # a query whose every hit is dropped
+    Dv = np.sort(rs.rand(nq, kin).astype(np.float32), axis=1)
+    d_ids, d_col, d_enc = _Dev(ids), _Dev(col), _Dev(np.zeros_like(ids))
+    assert L.dfx_encode_ids_dev(C.c_int64(ids.size), C.c_void_p(d_ids.ptr), C.c_int64(5), C.c_void_p(d_col.ptr),
+                                C.c_int32(2), C.c_void_p(d_enc.ptr), None) == 0
+    enc = d_enc.get()
+    drop = (col[np.maximum(ids, 0)] == 2) | (col[np.maximum(ids, 0)] == -2)
+    want = np.where(ids < 0, -1, (5 << 40) | ids | np.where(drop, 1 << 62, 0))
+    assert np.array_equal(enc, want)
+    d_D, d_oD, d_oI, d_cnt = _Dev(Dv), _Dev(np.zeros((nq, kout), np.float32)), _Dev(np.zeros((nq, kout), np.int64)), \
+        _Dev(np.zeros(nq, np.int32))
+    d_enc2 = _Dev(enc)
+    assert L.dfx_filter_compact_dev(C.c_int64(nq), C.c_int64(kin), C.c_int64(kout), C.c_void_p(d_D.ptr),
+                                    C.c_void_p(d_enc2.ptr), C.c_void_p(d_oD.ptr), C.c_void_p(d_oI.ptr),
+                                    C.c_void_p(d_cnt.ptr), None) == 0
+    oD, oI, cnt = d_oD.get(), d_oI.get(), d_cnt.get()
+    for q in range(nq):
+        keep = [j for j in range(kin) if ids[q, j] >= 0 and not drop[q, j]][:kout]
+        assert cnt[q] == len(keep)
+        assert np.array_equal(oI[q, :len(keep)], enc[q, keep]) and np.array_equal(oD[q, :len(keep)], Dv[q, keep])
+        assert (oI[q, len(keep):] == -1).all() and (oD[q, len(keep):] == np.finfo(np.float32).max).all()
+    assert cnt[3] == 0
+
+    # owner-decoded winners
+    d = 64
+    xb = rs.rand(300, d).astype(np.float32)
+    g = E.GpuIndex(E.KIND_FLAT, d, IP)
+    g.add(xb)
+    loc = rs.randint(0, 300, size=20).astype(np.int64)
+    tags = rs.randint(0, 3, size=20).astype(np.int64)
+    enc = (tags << 40) | loc
+    enc[::7] |= 1 << 62                                       # a drop flag does not change the owner
+    enc[5] = -1
+    out0 = rs.rand(20, d).astype(np.float32)
+    d_e, d_o = _Dev(enc), _Dev(out0)
+    assert L.dfx_reconstruct_dev(g._h, C.c_int64(20), C.c_void_p(d_e.ptr), C.c_int64(1), C.c_void_p(d_o.ptr), None) == 0
+    out = d_o.get()
+    own = (tags == 1) & (enc >= 0)
+    assert np.array_equal(out[own], xb[loc[own]]) and np.array_equal(out[~own], out0[~own])

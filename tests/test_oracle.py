@@ -170,3 +170,33 @@ def test_pq_decomposition_terms():
         approx = dis0 + ix.tvals[pos] + s
         exact = ((q.astype(np.float64) - recon[pos]) ** 2).sum()
         assert abs(approx - exact) <= 1e-4 * (1 + (q ** 2).sum() + (recon[pos] ** 2).sum())
+
+
+def test_cpu_baseline_matches_oracle(oracle_lib):
+    """the TIMED CPU baseline (oracle/cpu_ivfpq.c: sgemm coarse + threaded scan, free summation
+    order) against the bit-exact checker: same probe lists, distances within 1e-4 relative, ids
+    equal wherever the oracle's distances are separated by more than that"""
+    from oracle import cpu_baseline as CB
+    from oracle import oracle as O
+    from tests.conftest import clustered
+
+    rs = np.random.RandomState(5)
+    d, nlist, M, n = 128, 64, 32, 20000
+    xb = clustered(rs, n, d, ncl=80)
+    o = O.OracleIVFPQ(d, nlist, M, 8, coarse_metric=O.METRIC_L2)
+    o.train_niter = 4
+    o.train(xb[:6000])
+    o.add(xb)
+    xq = xb[:300] + 0.01 * rs.randn(300, d).astype(np.float32)
+    cb = CB.CpuIVFPQ(o.get_state(), threads=4)
+    for nprobe, k in ((8, 10), (1, 1), (nlist, 25)):
+        o.nprobe = nprobe
+        Do, Io = o.search(xq, k)
+        Dc, Ic = cb.search(xq, k, nprobe)
+        assert cb.last_ndis == o.last_ndis                      # same probe lists
+        fin = Do < 3e38
+        assert np.allclose(Dc[fin], Do[fin], rtol=1e-4, atol=1e-4) and ((Ic >= 0) == fin).all()
+        gap = np.abs(np.diff(Do, axis=1, append=3.4e38)) > 1e-3 * np.maximum(np.abs(Do), 1.0)
+        gap[:, 1:] &= gap[:, :-1]                               # separated from both neighbours
+        assert (Ic[gap & fin] == Io[gap & fin]).mean() > 0.999
+        assert (Ic == Io).mean() > 0.98
