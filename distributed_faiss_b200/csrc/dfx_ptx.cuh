@@ -59,6 +59,15 @@ __device__ __forceinline__ uint32_t dfx_ld_nc_u(const int32_t* p) {
 }
 
 // ---- shared memory by 32-bit shared-window address (see dfx_smem_addr)
+// L2 prefetch of the 128-byte line holding p (no register result, no scoreboard)
+__device__ __forceinline__ void dfx_prefetch_l2(const void* p) {
+#ifndef DFX_EMU
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#else
+    (void)p;
+#endif
+}
+
 __device__ __forceinline__ uint32_t dfx_smem_addr(const void* p) {
 #ifdef DFX_EMU
     return simt::smem_addr(p);

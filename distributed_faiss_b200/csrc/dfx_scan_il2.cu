@@ -1,6 +1,7 @@
 // dfx_scan_il2.cu -- launcher of the IVF-PQ (M == 32) table build + inverted-list scan, K3 + K4.
 // Kernel: dfx_scan_il2_dev.cuh.
 #include "dfx_scan_il2_dev.cuh"
+#include <cstdlib>
 
 template <bool REG>
 static void launch_il2(dfx_index* idx, const float* xq, int64_t qc, const int32_t* keys, int nprobe, int G,
@@ -10,9 +11,16 @@ static void launch_il2(dfx_index* idx, const float* xq, int64_t qc, const int32_
     auto kern = scan_pq_il2_kernel<REG>;
     DFX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     DFX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    // blocks the L2 prefetch cursor runs ahead of the register loads (0 = off; DFX_IL2_PREFETCH)
+    static const int pf_ahead = [] {
+        const char* e = getenv("DFX_IL2_PREFETCH");
+        const int v = e ? atoi(e) : 4;
+        return v < 0 ? 0 : (v > 32 ? 32 : v);
+    }();
     DFX_LAUNCH(kern, (unsigned)(qc * ngroups), IL2_THREADS, smem, st, xq, idx->codebooksT.as<float>(),
                idx->centroids.as<float>(), idx->cfg.d, idx->dsub, keys, nprobe, G, ngroups, idx->blk_off.as<int64_t>(),
-               idx->il_codes.as<uint4>(), idx->il_tvals.as<float>(), idx->il_ids.as<int32_t>(), k, cap, part, outD, outI);
+               idx->il_codes.as<uint4>(), idx->il_tvals.as<float>(), idx->il_ids.as<int32_t>(), k, cap, part, outD, outI,
+               pf_ahead);
 }
 
 // outD / outI: when ngroups == 1 and k <= 32 the kernel writes the final rows there and the

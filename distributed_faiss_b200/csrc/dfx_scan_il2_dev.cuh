@@ -102,7 +102,7 @@ scan_pq_il2_kernel(const float* __restrict__ Q, const float* __restrict__ cbT, c
                    int dsub, const int32_t* __restrict__ keys, int nprobe, int G, int ngroups,
                    const int64_t* __restrict__ blk_off, const uint4* __restrict__ il_codes,
                    const float* __restrict__ il_tvals, const int32_t* __restrict__ il_ids, int k, int cap,
-                   uint64_t* __restrict__ part, float* __restrict__ outD, int64_t* __restrict__ outI) {
+                   uint64_t* __restrict__ part, float* __restrict__ outD, int64_t* __restrict__ outI, int pf_ahead) {
     constexpr int THREADS = IL2_THREADS;
     DFX_DYN_SMEM(unsigned char, smem_raw, 128);
     float* s_lut = reinterpret_cast<float*>(smem_raw);                      // [256][64]
@@ -270,8 +270,25 @@ scan_pq_il2_kernel(const float* __restrict__ Q, const float* __restrict__ cbT, c
         }
         return true;
     };
+    // L2 prefetch cursor: runs pf_ahead blocks in front of the fetch cursor over the same block
+    // stream (lanes 0..7 touch the 8 code lines of the block, lane 8 its t-values line), so that
+    // the register loads two blocks ahead find their lines in L2 instead of waiting on DRAM
+    int pf_p = -1, pf_b = 0, pf_e = 0;
+    auto prefetch_next = [&]() {
+        if (pf_p >= np) return;
+        pf_b += IL2_NW;
+        while (pf_b >= pf_e) {
+            if (++pf_p >= np) return;
+            pf_b = s_lb[pf_p] + warp;
+            pf_e = s_le[pf_p];
+        }
+        if (lane < 8) dfx_prefetch_l2(reinterpret_cast<const unsigned char*>(il_codes) + (int64_t)pf_b * 1024 + lane * 128);
+        else if (lane == 8) dfx_prefetch_l2(il_tvals + (int64_t)pf_b * 32);
+    };
+    for (int i = 0; i < pf_ahead; i++) prefetch_next();
 #define IL2_FETCH(A, B, T, D0, POS)                                          \
     do {                                                                     \
+        if (pf_ahead) prefetch_next();                                       \
         if (next_block()) {                                                  \
             const uint4* pc_ = il_codes + (int64_t)cur_b * 64 + lane;        \
             A = dfx_ld_stream(pc_);                                          \

@@ -296,8 +296,7 @@ class ShardGroup:
                 done = torch.cuda.Event()
                 done.record(st)
                 main.wait_event(done)
-            for st in self._streams[:min(len(self._streams), S_loc)]:
-                all_packed.record_stream(st)
+            # (no record_stream: main waits for every side stream before anything reuses the buffer)
         else:
             for j, shard in enumerate(self.shards):
                 one(j, shard)
@@ -347,18 +346,19 @@ class ShardGroup:
             return D.numpy(), I.numpy()
         if self._pin_q is None or self._pin_q.shape != (nq, d):
             self._pin_q = torch.empty((nq, d), dtype=torch.float32, pin_memory=True)
-        nb = 12 * nq * k
+        off_I = _align8(4 * nq * k)
+        nb = off_I + 8 * nq * k
         if self._pin_out is None or self._pin_out.numel() != nb:
             self._pin_out = torch.empty((nb,), dtype=torch.uint8, pin_memory=True)
         self._pin_q.numpy()[...] = x
         x_t = self._pin_q.to(self.device, non_blocking=True)
         D, I = self.search(x_t, k, maximize, src)
         self._pin_out[:4 * nq * k].view(torch.float32).copy_(D.view(-1), non_blocking=True)
-        self._pin_out[4 * nq * k:].view(torch.int64).copy_(I.view(-1), non_blocking=True)
+        self._pin_out[off_I:].view(torch.int64).copy_(I.view(-1), non_blocking=True)
         torch.cuda.current_stream().synchronize()
         o = self._pin_out.numpy()
         return (o[:4 * nq * k].view(np.float32).reshape(nq, k).copy(),
-                o[4 * nq * k:].view(np.int64).reshape(nq, k).copy())
+                o[off_I:].view(np.int64).reshape(nq, k).copy())
 
 
 # =================================================================================================
