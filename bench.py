@@ -178,39 +178,88 @@ def recall_at_k(I, gt, ok=None):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    """SM clock and throttle reasons sampled DURING the timed regions (B200_PROFILING.md): an
+    in-process NVML thread (5 ms period; the timed region of the default run is ~0.15 s, too short
+    for an `nvidia-smi -lms` child to even start), `nvidia-smi` as the fallback.  `start()` returns
+    once the first sample is in."""
+
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+               0x80: "hw_power_brake_slowdown"}
 
     def __init__(self, gpu_index):
-        self.rows = []
-        self.proc = None
         self.gpu = gpu_index
+        self.sm, self.mx, self.mask = [], [], 0
+        self._stop = threading.Event()
+        self.t = None
+        self.source = None
 
-    def start(self):
+    def _handle(self):
+        import pynvml
+        import torch
+
+        pynvml.nvmlInit()
+        try:
+            uuid = str(torch.cuda.get_device_properties(self.gpu).uuid)
+            if not uuid.startswith("GPU-"):
+                uuid = "GPU-" + uuid
+            return pynvml, pynvml.nvmlDeviceGetHandleByUUID(uuid)
+        except Exception:
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            idx = int(vis.split(",")[self.gpu]) if vis and vis.split(",")[self.gpu].isdigit() else self.gpu
+            return pynvml, pynvml.nvmlDeviceGetHandleByIndex(idx)
+
+    def _loop_nvml(self, nv, h):
+        mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        while not self._stop.is_set():
+            self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+            self.mx.append(float(mx))
+            try:
+                self.mask |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
+            except Exception:
+                self.mask |= int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+            time.sleep(0.005)
+
+    def _loop_smi(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.gpu), "-lms", "20"], stdout=subprocess.PIPE, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
-        except Exception:
-            self.proc = None
-
-    def _read(self):
+        bits = [0x8, 0x40, 0x20, 0x4]
+        self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.gpu), "-lms", "20"], stdout=subprocess.PIPE, text=True)
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            r = [c.strip() for c in line.split(",")]
+            if r and r[0].replace(".", "").isdigit():
+                self.sm.append(float(r[0]))
+                if len(r) > 1 and r[1].replace(".", "").isdigit():
+                    self.mx.append(float(r[1]))
+                for i, b in enumerate(bits):
+                    if len(r) > 2 + i and r[2 + i] == "Active":
+                        self.mask |= b
+            if self._stop.is_set():
+                break
+        self.proc.terminate()
+
+    def start(self):
+        try:
+            nv, h = self._handle()
+            nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+            self.source = "nvml"
+            self.t = threading.Thread(target=self._loop_nvml, args=(nv, h), daemon=True)
+        except Exception:
+            self.source = "nvidia-smi"
+            self.t = threading.Thread(target=self._loop_smi, daemon=True)
+        self.t.start()
+        t0 = time.time()
+        while not self.sm and time.time() - t0 < 10.0:   # first sample before the timed region starts
+            time.sleep(0.005)
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i] == "Active" for r in self.rows)]
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+        self._stop.set()
+        if self.t is not None:
+            self.t.join(timeout=2.0)
+        reasons = [n for b, n in self.REASONS.items() if self.mask & b]
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None,
+                "sm_max_mhz": max(self.mx) if self.mx else None, "reasons": reasons, "samples": len(self.sm),
+                "source": self.source}
 
 
 # ---------------------------------------------------------------------------------------------

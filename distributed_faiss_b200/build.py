@@ -8,6 +8,7 @@ parity with oracle/dfx_oracle.c); the compiler must not contract anything else.
 """
 from __future__ import annotations
 
+import hashlib
 import os
 import subprocess
 import sys
@@ -26,17 +27,44 @@ FLAGS = [
 ]
 
 
-def _deps_mtime():
-    m = 0.0
+_HASH_MARK = b"dfx-src-sha256="
+
+
+def source_hash() -> str:
+    """sha256 over every source the library is compiled from (csrc/, include/) and the compiler
+    flags.  It is compiled into the library (`dfx_version()` ends with it), so a stale binary is
+    recognised by content -- file times do not survive a copy of the tree to another machine."""
+    h = hashlib.sha256()
+    h.update(" ".join(FLAGS).encode())
     for root in (CSRC, os.path.join(HERE, "..", "include")):
-        for f in os.listdir(root):
+        for f in sorted(os.listdir(root)):
             if f.endswith((".cu", ".cuh", ".h")):
-                m = max(m, os.path.getmtime(os.path.join(root, f)))
-    return m
+                h.update(f.encode())
+                with open(os.path.join(root, f), "rb") as fh:
+                    h.update(fh.read())
+    return h.hexdigest()[:32]
+
+
+def embedded_hash(path: str = LIB):
+    """the source hash a built library carries (None: no library, or one built without it)."""
+    try:
+        with open(path, "rb") as fh:
+            blob = fh.read()
+    except OSError:
+        return None
+    i = blob.find(_HASH_MARK)
+    if i < 0:
+        return None
+    return blob[i + len(_HASH_MARK): i + len(_HASH_MARK) + 32].decode("ascii", "replace")
+
+
+def is_current() -> bool:
+    return embedded_hash() == source_hash()
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= _deps_mtime():
+    want = source_hash()
+    if not force and embedded_hash() == want:
         return LIB
     if not os.path.exists(NVCC):
         raise RuntimeError(f"nvcc not found at {NVCC}; libdfx.so cannot be built")
@@ -45,6 +73,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     def compile_one(src):
         obj = os.path.join(OBJ, src.replace(".cu", ".o"))
         cmd = [NVCC, *FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        if src == "dfx_api.cu":
+            cmd.insert(1, f'-DDFX_SRC_HASH="{want}"')
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         r = subprocess.run(cmd, capture_output=True, text=True)
@@ -61,6 +91,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    if embedded_hash() != want:
+        raise RuntimeError("libdfx.so was built but does not carry the expected source hash")
     return LIB
 
 

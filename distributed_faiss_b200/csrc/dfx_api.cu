@@ -51,7 +51,11 @@ struct DeviceGuard {
 extern "C" {
 
 const char* dfx_last_error(void) { return g_last_error.c_str(); }
-const char* dfx_version(void) { return "dfx 0.1 (sm_100a)"; }
+#ifndef DFX_SRC_HASH
+#define DFX_SRC_HASH "unknown"
+#endif
+// ends with the hash of the sources the library was compiled from (build.py: source_hash)
+const char* dfx_version(void) { return "dfx 0.2 (sm_100a) dfx-src-sha256=" DFX_SRC_HASH; }
 int64_t dfx_launch_count(void) { return (int64_t)g_dfx_launches.load(); }
 int dfx_debug_il_byte(int layout, int v, int m) { return dfx_il_byte_of(layout, v & 31, m & 31); }
 
@@ -120,6 +124,14 @@ int dfx_set_param(dfx_index* idx, const char* name, double value) {
     else if (n == "rows_inflight") {
         DFX_REQUIRE(value == 0 || value == 4 || value == 8, "rows_inflight must be 0 (by row size), 4 or 8");
         idx->rows_inflight = (int)value;
+    }
+    else if (n == "il2_threads") {
+        DFX_REQUIRE(value == 0 || value == 256 || value == 512, "il2_threads must be 0 (default), 256 or 512");
+        idx->il2_threads = (int)value;
+    }
+    else if (n == "il2_prefetch") {
+        DFX_REQUIRE(value >= -1 && value <= 32, "il2_prefetch must be -1 (default) or 0..32 blocks");
+        idx->il2_prefetch = (int)value;
     }
     else throw DfxError{"unknown parameter " + n};
     DFX_API_END

@@ -50,6 +50,8 @@ struct dfx_index {
     bool tc_ready = false;
     bool tc_enabled = true;
     int rows_inflight = 0;      // vectors in flight per warp of scan_rows_kernel: 0 = by row size, else 4 / 8
+    int il2_threads = 0;        // scan_pq_il2 CTA shape: 0 = default (env DFX_IL2_THREADS or 256), 256, 512
+    int il2_prefetch = -1;      // L2 prefetch distance in blocks: -1 = default (env DFX_IL2_PREFETCH or 4)
     bool flat_tc = true;        // FLAT: search through the tensor-core screening (dfx_tc_flat_candidates)
     int64_t tc_flat_rows = -1;  // rows covered by the bf16 planes of a FLAT index (-1: none)
 

@@ -24,8 +24,10 @@
 //     bitonic network over shuffles, the remainder stays queued.
 //     Ids are not streamed: the queue holds positions, ids are gathered when the queue is
 //     merged (one latency per merge) or on an exact tie with the k-th best.
-//   * The block stream of a warp runs across list boundaries with two blocks in flight, so a new
-//     list does not expose a DRAM latency (a warp owns only ~7 blocks of each list).
+//   * A warp scans a CONTIGUOUS eighth of the CTA's blocks (the probed lists laid end to end),
+//     two blocks in flight in registers and an L2 prefetch pf_ahead blocks further in the same
+//     segment; the stream crosses list boundaries, the head of the next segment is prefetched when
+//     a segment is entered.
 //   * K3 fused (round 2): the CTA builds its query's table in the prologue -- lut[m][j] =
 //     -2 * ip_seq(q_m, P[m][j]) from the transposed codebook PT[j][m][dsub] (L2-resident, 128 KB),
 //     warp w produces rows j = w, w+8, ... with lane = m, so codebook reads are 512-byte runs and
@@ -39,7 +41,7 @@
 #include "dfx_topk.cuh"
 #include "dfx_ptx.cuh"
 
-constexpr int IL2_THREADS = 256;             // 8 warps; 3 CTAs per SM (64 KB table each)
+constexpr int IL2_THREADS = 256;             // default: 8 warps; 3 CTAs per SM (64 KB table each)
 constexpr int IL2_LUT_BYTES = 256 * 64 * 4;  // wide table of one query
 constexpr int IL2_QCAP = 64;                 // queue slots per warp (register top-k path)
 constexpr int IL2_MAXG = 16;                 // probes per CTA (choose_group caps G at 16)
@@ -96,14 +98,13 @@ __device__ __noinline__ Il2Flushed il2_flush(uint64_t kept, uint64_t* queue, int
 // REG: k <= 32, register-resident top-k;  !REG: WarpTopK buffers in shared memory (any k)
 // Q [nq][d] queries; cbT: transposed codebook PT[j][m][dsub]; cent [nlist][d]; d = 32 * dsub.
 // outD / outI != nullptr (requires ngroups == 1): final faiss-style rows are written directly.
-template <bool REG>
-__global__ void __launch_bounds__(IL2_THREADS, 3)
+template <bool REG, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB)
 scan_pq_il2_kernel(const float* __restrict__ Q, const float* __restrict__ cbT, const float* __restrict__ cent, int d,
                    int dsub, const int32_t* __restrict__ keys, int nprobe, int G, int ngroups,
                    const int64_t* __restrict__ blk_off, const uint4* __restrict__ il_codes,
                    const float* __restrict__ il_tvals, const int32_t* __restrict__ il_ids, int k, int cap,
                    uint64_t* __restrict__ part, float* __restrict__ outD, int64_t* __restrict__ outI, int pf_ahead) {
-    constexpr int THREADS = IL2_THREADS;
     DFX_DYN_SMEM(unsigned char, smem_raw, 128);
     float* s_lut = reinterpret_cast<float*>(smem_raw);                      // [256][64]
     uint64_t* s_buf = reinterpret_cast<uint64_t*>(smem_raw + IL2_LUT_BYTES);  // queues / WarpTopK buffers
@@ -111,6 +112,7 @@ scan_pq_il2_kernel(const float* __restrict__ Q, const float* __restrict__ cbT, c
     __shared__ int s_lb[IL2_MAXG], s_le[IL2_MAXG];  // first / end block of each probed list
     __shared__ float s_ld0[IL2_MAXG];               // |q - c|^2 of each probed list
     __shared__ int s_lkey[IL2_MAXG];
+    __shared__ int s_cum[IL2_MAXG + 1];             // blocks of the probed lists before list p
 
     constexpr int IL2_NW = THREADS / 32;
     const int64_t q = blockIdx.x / ngroups;
@@ -158,6 +160,14 @@ scan_pq_il2_kernel(const float* __restrict__ Q, const float* __restrict__ cbT, c
         }
     }
     __syncthreads();  // s_lkey visible (and the table complete)
+    if (tid == THREADS - 1) {  // the CTA's block stream: the probed lists end to end
+        int c = 0;
+        for (int p = 0; p < np; p++) {
+            s_cum[p] = c;
+            c += s_le[p] - s_lb[p];
+        }
+        s_cum[np] = c;
+    }
     // ---- K3, part 2: exact |q - c|^2 of the probed lists, canonical warp-dot order
     for (int p = warp; p < np; p += IL2_NW) {
         const int l = s_lkey[p];
@@ -254,50 +264,71 @@ scan_pq_il2_kernel(const float* __restrict__ Q, const float* __restrict__ cbT, c
         }
     };
 
-    // ---- the warp's block stream: blocks lb + warp, + NW, ... of each probed list, in probe order
-    int cur_p = -1, cur_b = 0, cur_e = 0;
+    // ---- the warp's block stream: a CONTIGUOUS eighth of the CTA's blocks (the probed lists laid
+    // end to end, s_cum), so that the cursor is one increment and one compare per block, the L2
+    // prefetch is "the same segment, pf_ahead blocks further" and the warps finish together.
+    // (The profile of the strided walk -- blocks lb + warp, + 8, ... of every list, with a second
+    // cursor for the prefetch -- showed ~68 bookkeeping instructions per block next to the 82 of
+    // the lookups and the tree.)  A warp's range spans one or two lists; entering a segment is the
+    // rare path and prefetches the head of the segment after it.
+    const int nblk_cta = s_cum[np];
+    const int r0 = (int)(((int64_t)nblk_cta * warp) / IL2_NW);
+    int rem = (int)(((int64_t)nblk_cta * (warp + 1)) / IL2_NW) - r0;  // blocks not yet assigned to a segment
+    int cur_p = 0, cur_b = 0, cur_e = 0;
     float cur_d0 = 0.f;
-    auto next_block = [&]() -> bool {
-        cur_b += IL2_NW;
-        while (cur_b >= cur_e) {
-            if (++cur_p >= np) {
-                cur_p = np;
-                return false;
-            }
-            cur_b = s_lb[cur_p] + warp;
-            cur_e = s_le[cur_p];
+    const bool pf_lane = pf_ahead > 0 && lane < 9;  // lanes 0..7: the 8 code lines of a block, lane 8: its t-values
+    const unsigned char* pf_base = (lane < 8) ? reinterpret_cast<const unsigned char*>(il_codes) + lane * 128
+                                              : reinterpret_cast<const unsigned char*>(il_tvals);
+    const int pf_stride = (lane < 8) ? 1024 : 128;
+    auto prefetch_head = [&](int b, int n) {  // first min(n, pf_ahead) blocks of a segment
+        n = n < pf_ahead ? n : pf_ahead;
+        if (pf_lane)
+            for (int i = 0; i < n; i++) dfx_prefetch_l2(pf_base + (int64_t)(b + i) * pf_stride);
+    };
+    auto peek_next_segment = [&]() {  // prefetch the head of the segment that follows the current one
+        if (rem <= 0 || pf_ahead == 0) return;
+        int p2 = cur_p + 1;
+        while (s_le[p2] == s_lb[p2]) p2++;  // rem > 0: a non-empty list lies ahead
+        const int len = s_le[p2] - s_lb[p2];
+        prefetch_head(s_lb[p2], len < rem ? len : rem);
+    };
+    if (rem > 0) {
+        while (s_cum[cur_p + 1] <= r0) cur_p++;  // the list holding block r0 of the CTA's stream
+        cur_b = s_lb[cur_p] + (r0 - s_cum[cur_p]);
+        const int len = min(s_le[cur_p] - cur_b, rem);
+        cur_e = cur_b + len;
+        rem -= len;
+        cur_d0 = s_ld0[cur_p];
+        prefetch_head(cur_b, len);
+        peek_next_segment();
+    }
+    // next block of the range, or -1
+    auto next_block = [&]() -> int {
+        if (cur_b == cur_e) {  // segment exhausted (once or twice per warp)
+            if (rem <= 0) return -1;
+            do cur_p++; while (s_le[cur_p] == s_lb[cur_p]);
+            cur_b = s_lb[cur_p];
+            const int len = min(s_le[cur_p] - cur_b, rem);
+            cur_e = cur_b + len;
+            rem -= len;
             cur_d0 = s_ld0[cur_p];
+            peek_next_segment();
         }
-        return true;
+        return cur_b++;
     };
-    // L2 prefetch cursor: runs pf_ahead blocks in front of the fetch cursor over the same block
-    // stream (lanes 0..7 touch the 8 code lines of the block, lane 8 its t-values line), so that
-    // the register loads two blocks ahead find their lines in L2 instead of waiting on DRAM
-    int pf_p = -1, pf_b = 0, pf_e = 0;
-    auto prefetch_next = [&]() {
-        if (pf_p >= np) return;
-        pf_b += IL2_NW;
-        while (pf_b >= pf_e) {
-            if (++pf_p >= np) return;
-            pf_b = s_lb[pf_p] + warp;
-            pf_e = s_le[pf_p];
-        }
-        if (lane < 8) dfx_prefetch_l2(reinterpret_cast<const unsigned char*>(il_codes) + (int64_t)pf_b * 1024 + lane * 128);
-        else if (lane == 8) dfx_prefetch_l2(il_tvals + (int64_t)pf_b * 32);
-    };
-    for (int i = 0; i < pf_ahead; i++) prefetch_next();
+    const uint4* pc_lane = il_codes + lane;
+    const float* pt_lane = il_tvals + lane;
 #define IL2_FETCH(A, B, T, D0, POS)                                          \
     do {                                                                     \
-        if (pf_ahead) prefetch_next();                                       \
-        if (next_block()) {                                                  \
-            const uint4* pc_ = il_codes + (int64_t)cur_b * 64 + lane;        \
+        POS = next_block();                                                  \
+        if (POS >= 0) {                                                      \
+            const uint4* pc_ = pc_lane + (int64_t)POS * 64;                  \
             A = dfx_ld_stream(pc_);                                          \
             B = dfx_ld_stream(pc_ + 32);                                     \
-            T = dfx_ld_stream_f(il_tvals + (int64_t)cur_b * 32 + lane);      \
+            T = dfx_ld_stream_f(pt_lane + (int64_t)POS * 32);                \
             D0 = cur_d0;                                                     \
-            POS = cur_b;                                                     \
-        } else {                                                             \
-            POS = -1;                                                        \
+            if (pf_lane && POS + pf_ahead < cur_e)                           \
+                dfx_prefetch_l2(pf_base + (int64_t)(POS + pf_ahead) * pf_stride); \
         }                                                                    \
     } while (0)
 

@@ -36,11 +36,11 @@ __device__ __forceinline__ void dfx_block_bitonic_sort(uint64_t* s, int P) {
 // Loader:  __device__ uint64_t operator()(int64_t row, int e) const   (DFX_COMP_NONE = no candidate)
 // Writer:  __device__ void operator()(int64_t row, int j, uint64_t comp) const   (j in [0,k))
 // dynamic smem: P * 8 bytes with P = pow2 >= max(k, min(n, sort_cap))
+// One row by the whole CTA (every thread calls it with the same arguments; s_out = P * 8 bytes of
+// shared memory).  A caller that selects several rows in a loop puts a __syncthreads() between them.
 template <int THREADS, class Loader, class Writer>
-__global__ void __launch_bounds__(THREADS) dfx_select_rows_kernel(Loader ld, Writer wr, int n, int k,
-                                                                 int P, int sort_cap) {
-    DFX_DYN_SMEM(unsigned char, dfx_sel_smem, 16);
-    uint64_t* s_out = reinterpret_cast<uint64_t*>(dfx_sel_smem);
+__device__ __forceinline__ void dfx_select_row(const Loader& ld, const Writer& wr, int64_t row, int n, int k, int P,
+                                               int sort_cap, uint64_t* s_out) {
     __shared__ int s_hist[256];
     __shared__ int s_cnt;
     __shared__ int s_valid;
@@ -48,7 +48,6 @@ __global__ void __launch_bounds__(THREADS) dfx_select_rows_kernel(Loader ld, Wri
     __shared__ int s_krem;
     __shared__ int s_done;
 
-    const int64_t row = blockIdx.x;
     const int tid = threadIdx.x;
 
     if (n <= sort_cap) {
@@ -135,6 +134,13 @@ __global__ void __launch_bounds__(THREADS) dfx_select_rows_kernel(Loader ld, Wri
     __syncthreads();
     dfx_block_bitonic_sort<THREADS>(s_out, P);
     for (int j = tid; j < k; j += THREADS) wr(row, j, (j < kprime) ? s_out[j] : DFX_COMP_NONE);
+}
+
+template <int THREADS, class Loader, class Writer>
+__global__ void __launch_bounds__(THREADS) dfx_select_rows_kernel(Loader ld, Writer wr, int n, int k,
+                                                                 int P, int sort_cap) {
+    DFX_DYN_SMEM(unsigned char, dfx_sel_smem, 16);
+    dfx_select_row<THREADS>(ld, wr, (int64_t)blockIdx.x, n, k, P, sort_cap, reinterpret_cast<uint64_t*>(dfx_sel_smem));
 }
 
 // host-side launch helper

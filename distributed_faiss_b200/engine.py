@@ -63,6 +63,11 @@ def lib():
                 raise RuntimeError(
                     f"{LIB_PATH} is missing: build it with `python -m distributed_faiss_b200.build` "
                     "(or __graft_entry__.build()). There is no CPU fallback for the search path.")
+            if LIB_PATH == os.path.join(_HERE, "libdfx.so") and os.path.isdir(os.path.join(_HERE, "csrc")):
+                # a binary that does not match the sources next to it is rebuilt, never used silently
+                from . import build as _build
+                if not _build.is_current():
+                    _build.build()
             L = C.CDLL(LIB_PATH)
             L.dfx_last_error.restype = C.c_char_p
             L.dfx_version.restype = C.c_char_p

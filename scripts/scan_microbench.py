@@ -34,25 +34,35 @@ def main():
     xq = synth.rows(0, 12288, rows_t=q_rows, noise_stream=7)
     idx.nprobe = int(os.environ.get("MB_NPROBE", 8))
     out = {"label": label, "info": info}
-    for B in (4096,):
-        batches = [xq[i * B:(i + 1) * B].contiguous() for i in range(12288 // B)]
-        for b in batches:
-            idx.search_dev(b, 10)
-        torch.cuda.synchronize()
-        ndis = idx.last_stats()["ndis"]
-        idx.profile(True)
-        idx.profile_read(True)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        n = 30
-        for i in range(n):
-            idx.search_dev(batches[i % len(batches)], 10)
-        e1.record()
-        torch.cuda.synchronize()
-        ms, nl = idx.profile_read(True)
-        idx.profile(False)
-        out[f"B{B}"] = {"scan_ms_per_launch": ms / nl, "search_ms": e0.elapsed_time(e1) / n,
-                        "algorithmic_GBps": ndis * 32 / (ms / nl) / 1e6, "frac_of_6568": ndis * 32 / (ms / nl) / 1e6 / 6568.4}
+    # MB_VARIANTS="threads:prefetch,..." e.g. "256:4,256:0,512:4" (dfx_set_param il2_threads / il2_prefetch)
+    variants = [tuple(int(x) for x in v.split(":")) for v in os.environ.get("MB_VARIANTS", "0:-1").split(",")]
+    ref = None
+    for (thr, pf) in variants:
+      idx.set_param("il2_threads", thr)
+      idx.set_param("il2_prefetch", pf)
+      for B in (4096,):
+          batches = [xq[i * B:(i + 1) * B].contiguous() for i in range(12288 // B)]
+          for b in batches:
+              idx.search_dev(b, 10)
+          torch.cuda.synchronize()
+          ndis = idx.last_stats()["ndis"]
+          idx.profile(True)
+          idx.profile_read(True)
+          e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+          e0.record()
+          n = 30
+          for i in range(n):
+              idx.search_dev(batches[i % len(batches)], 10)
+          e1.record()
+          torch.cuda.synchronize()
+          ms, nl = idx.profile_read(True)
+          idx.profile(False)
+          Dv, Iv = idx.search_dev(batches[0], 10)
+          if ref is None:
+              ref = (Dv.clone(), Iv.clone())
+          same = bool(torch.equal(Dv, ref[0]) and torch.equal(Iv, ref[1]))
+          out[f"t{thr}_pf{pf}_B{B}"] = {"same_as_first_variant": same, "scan_ms_per_launch": ms / nl, "search_ms": e0.elapsed_time(e1) / n,
+                          "algorithmic_GBps": ndis * 32 / (ms / nl) / 1e6, "frac_of_6568": ndis * 32 / (ms / nl) / 1e6 / 6568.4}
     print(json.dumps(out))
 
 

@@ -27,6 +27,10 @@ def test_library_builds_and_exports_header_symbols():
         assert hasattr(lib, name), f"{name} declared in include/dfx.h but not exported"
     assert sorted(engine.EXPORTED_SYMBOLS) == declared
     assert b"sm_100a" in engine.lib().dfx_version()
+    # the library carries the hash of the sources it was compiled from (build.py rebuilds on mismatch)
+    from distributed_faiss_b200 import build
+    assert build.embedded_hash() == build.source_hash()
+    assert engine.lib().dfx_version().decode().endswith(build.source_hash())
 
 
 def test_no_cpu_fallback():
