@@ -100,6 +100,8 @@ void dfx_destroy(dfx_index* idx) {
             cudaEventDestroy(e.first);
             cudaEventDestroy(e.second);
         }
+        if (idx->tc_stat_ev) cudaEventDestroy(idx->tc_stat_ev);
+        if (idx->tc_stat_h) cudaFreeHost(idx->tc_stat_h);
         delete idx;
     }
 }
@@ -125,6 +127,12 @@ int dfx_set_param(dfx_index* idx, const char* name, double value) {
         DFX_REQUIRE(value == 0 || value == 4 || value == 8, "rows_inflight must be 0 (by row size), 4 or 8");
         idx->rows_inflight = (int)value;
     }
+    else if (n == "tc_screen_mode") {  // 0 = AUTO, 1 = FAST (one fp16 MMA), 2 = PRECISE (hi/lo split, three MMAs)
+        DFX_REQUIRE(value == 0 || value == 1 || value == 2, "tc_screen_mode must be 0 (auto), 1 (fast) or 2 (precise)");
+        idx->tc_mode = (int)value;
+        idx->tc_fast = value == 1;
+        idx->tc_stat_pending = false;
+    }
     else if (n == "il2_threads") {
         DFX_REQUIRE(value == 0 || value == 256 || value == 512, "il2_threads must be 0 (default), 256 or 512");
         idx->il2_threads = (int)value;
@@ -133,6 +141,33 @@ int dfx_set_param(dfx_index* idx, const char* name, double value) {
         DFX_REQUIRE(value >= -1 && value <= 32, "il2_prefetch must be -1 (default) or 0..32 blocks");
         idx->il2_prefetch = (int)value;
     }
+    else throw DfxError{"unknown parameter " + n};
+    DFX_API_END
+}
+
+int dfx_get_param(dfx_index* idx, const char* name, double* value) {
+    DFX_API_BEGIN
+    DFX_REQUIRE(idx && name && value, "null argument");
+    std::string n(name);
+    if (n.rfind("tc_stat_", 0) == 0 || n == "tc_fast") {
+        DeviceGuard g(idx->cfg.device);
+        dfx_tc_stats_sync(idx);  // fold the outstanding launch statistics in (AUTO precision)
+    }
+    if (n == "kmeans_niter") *value = idx->kmeans_niter;
+    else if (n == "max_points_per_centroid") *value = idx->max_points_per_centroid;
+    else if (n == "train_seed") *value = (double)idx->train_seed;
+    else if (n == "tensor_cores") *value = idx->tc_enabled;
+    else if (n == "tc_screen_mode") *value = idx->tc_mode;
+    else if (n == "tc_fast") *value = idx->tc_fast;
+    else if (n == "tc_cmax2") *value = idx->tc_cmax2;
+    else if (n == "tc_stat_rows") *value = (double)idx->tc_last_rows;
+    else if (n == "tc_stat_overflow") *value = (double)idx->tc_last_overflow;
+    else if (n == "tc_stat_fast_would") *value = (double)idx->tc_last_fast_would;
+    else if (n == "flat_tensor_cores") *value = idx->flat_tc;
+    else if (n == "interleaved") *value = idx->il_enabled;
+    else if (n == "il2_threads") *value = idx->il2_threads;
+    else if (n == "il2_prefetch") *value = idx->il2_prefetch;
+    else if (n == "rows_inflight") *value = idx->rows_inflight;
     else throw DfxError{"unknown parameter " + n};
     DFX_API_END
 }

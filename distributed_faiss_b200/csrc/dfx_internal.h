@@ -44,16 +44,28 @@ struct dfx_index {
     DevBuf codebooksT;  // [ksub][M][dsub]: the order the fused table build reads (dfx_scan_il2.cu)
     bool cbT_valid = false;
 
-    // tensor-core coarse quantizer (dfx_tc.cu): bf16 hi/lo planes and screening workspace
-    DevBuf tc_cent, tc_cent_tmp, tc_q, tc_gmin, tc_gmin2, tc_gargc, tc_groups, tc_cand, tc_qn, tc_amb;
+    // tensor-core coarse quantizer (dfx_tc.cu): fp16 copies (1 or 2 planes) and screening workspace
+    DevBuf tc_cent, tc_cent_tmp, tc_q, tc_qmult, tc_gmin, tc_gmin2, tc_gargc, tc_groups, tc_cand, tc_qn, tc_amb, tc_ovf;
     float tc_cmax2 = 0.f;
+    float tc_cscale = 1.f;      // power-of-two scale of the fp16 copy tc_cent
+    // screening precision (dfx_tc.cu): tc_mode 0 = AUTO, 1 = FAST (one fp16 MMA per k-step),
+    // 2 = PRECISE (hi/lo split, three MMAs).  AUTO starts PRECISE and moves to FAST once a launch
+    // shows that FAST's wider tolerance would not overflow the kept groups (and back if it does).
+    int tc_mode = 0;
+    bool tc_fast = false;       // the precision the next screening launch uses (AUTO state)
+    int tc_cent_npl = 0;        // planes currently held by tc_cent (0: none)
+    int32_t* tc_stat_h = nullptr;      // pinned [2]: {overflow rows, rows that FAST would overflow} of a past launch
+    cudaEvent_t tc_stat_ev = nullptr;
+    bool tc_stat_pending = false, tc_stat_fast = false;
+    int64_t tc_stat_rows = 0;
+    int64_t tc_last_rows = 0, tc_last_overflow = 0, tc_last_fast_would = 0;  // of the last launch polled
     bool tc_ready = false;
     bool tc_enabled = true;
     int rows_inflight = 0;      // vectors in flight per warp of scan_rows_kernel: 0 = by row size, else 4 / 8
     int il2_threads = 0;        // scan_pq_il2 CTA shape: 0 = default (env DFX_IL2_THREADS or 256), 256, 512
     int il2_prefetch = -1;      // L2 prefetch distance in blocks: -1 = default (env DFX_IL2_PREFETCH or 4)
     bool flat_tc = true;        // FLAT: search through the tensor-core screening (dfx_tc_flat_candidates)
-    int64_t tc_flat_rows = -1;  // rows covered by the bf16 planes of a FLAT index (-1: none)
+    int64_t tc_flat_rows = -1;  // rows covered by the fp16 copy of a FLAT index (-1: none)
 
     // scan-kernel profiling (dfx_profile_enable)
     bool prof_on = false;
@@ -156,6 +168,7 @@ bool dfx_launch_scan_pq_il2(dfx_index* idx, const float* xq, int64_t qc, const i
 
 // ---- dfx_tc.cu
 bool dfx_tc_supported(int d);
+void dfx_tc_stats_sync(dfx_index* idx);  // wait for and fold in the statistics of the last screening launch
 void dfx_tc_prepare_centroids(dfx_index* idx, cudaStream_t st);
 void dfx_tc_coarse_search(dfx_index* idx, const float* d_x, int64_t nq, int nprobe, int32_t* keys,
                           cudaStream_t st);

@@ -5,24 +5,33 @@
 // `quantizer.assign` (IndexIVF::add, index.py:425).
 //
 // Scheme ("screen on tensor cores, decide in canonical fp32"):
-//   1. fp32 operands are split into bf16 hi + lo planes; q.c ~= qh.ch + ql.ch + qh.cl is
-//      accumulated in fp32 in TMEM by tcgen05.mma (relative error ~1e-6, the ql.cl term
-//      ~2^-18 is dropped).
+//   1. both operands are scaled by a power of two (queries per row, the table as a whole, so that
+//      every row norm lands in [2^13, 2^14)) and rounded to fp16; q.c ~= (qh.ch) / (sq sc) is
+//      accumulated in fp32 in TMEM by ONE tcgen05.mma per k-step.  The rounding error is bounded
+//      rigorously: |q.c - screen| <= |q||c| (2^-10 + 2^-13)  (two 2^-11 relative roundings per
+//      product, fp32 accumulation), see screen_tol.  (Round 1 used a 3-MMA bf16 hi/lo split with a
+//      1e-5 error; the decide stage makes the result exact for ANY bounded error, and a model of the
+//      bench data put the extra exact evaluations of the 100x looser bound at +0.5 per query, for
+//      a third of the tensor-core work.)
 //   2. the epilogue turns each 128x128 accumulator tile into ranking values
 //      (L2: |c|^2 - 2 q.c, IP: -q.c) and keeps only the MINIMUM of every group of 32
 //      consecutive centroids -> gmin[nq][nlist/32]  (32x less traffic than the full matrix).
 //   3. the G = nprobe + margin groups with the smallest minima are selected exactly
-//      (dfx_select.cuh).  Every true top-nprobe centroid lies in one of the nprobe groups
-//      with the smallest group minimum; `margin` absorbs the 1e-6 screening error.
-//   4. the G*32 candidate centroids are re-evaluated in the CANONICAL fp32 order
+//      (dfx_select.cuh).  Every true top-nprobe centroid lies in a group whose minimum is within
+//      the tolerance of the nprobe-th smallest minimum; if the G-th selected group is still within
+//      it (more than `margin` near-ties, e.g. duplicate centroids) the row is re-done exactly by
+//      tc_exact_rows_kernel -- nothing is ever dropped silently.
+//   4. the candidate centroids are re-evaluated in the CANONICAL fp32 order
 //      (seq-k FMA, identical to oracle/dfx_oracle.c) and the final top-nprobe / argmin is
 //      taken on those exact values -> the probe lists are bit-identical to the oracle's.
 //
 // One CTA = 6 warps: warp 0 TMA producer, warp 1 TMEM allocator + single-thread MMA issuer,
-// warps 2..5 epilogue (one TMEM lane == one query row per thread).  A (query planes) stays
-// resident in shared memory, B (centroid planes) streams through a ring of 16 KB stages, two
-// TMEM accumulator buffers overlap the epilogue of tile i with the MMAs of tile i+1.
+// warps 2..5 epilogue (one TMEM lane == one query row per thread).  d <= 256: A (the query tile)
+// stays resident in shared memory and B (centroids) streams through a ring of 16 KB stages;
+// larger d (config C4, d = 768): A and B k-atoms stream through the ring together.  Two TMEM
+// accumulator buffers overlap the epilogue of tile i with the MMAs of tile i+1.
 #include "dfx_internal.h"
+#include <utility>
 #include "dfx_select.cuh"
 #include "dfx_topk.cuh"
 #include "dfx_ptx.cuh"
@@ -77,7 +86,7 @@ __device__ __forceinline__ void tc_alloc(uint32_t* smem_dst, uint32_t ncols) {
 __device__ __forceinline__ void tc_dealloc(uint32_t taddr, uint32_t ncols) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
-__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                             uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -90,6 +99,36 @@ __device__ __forceinline__ void tc_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
                      smem_u32(bar))
                  : "memory");
+}
+// (bits(v) & mask) | J in one LOP3 (mask in a register, J an immediate)
+template <int J>
+__device__ __forceinline__ float tc_pack_col(float v, uint32_t mask) {
+    uint32_t r;
+    asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(r) : "r"(__float_as_uint(v)), "r"(mask), "n"(J));
+    return __uint_as_float(r);
+}
+__device__ __forceinline__ float tc_min3(float a, float b, float c) {
+    float r;
+    asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+}
+// The two smallest of the 32 packed ranking values of one TMEM chunk, pairwise with the 3-input
+// min of sm_100 (FMNMX3): per pair lo / hi, m2 = min(m2, max(m1, lo), hi), m1 = min(m1, lo) --
+// 5 FMNMX + 2 LOP3 per pair on the ALU pipe, which bounds the FAST kernel (round 1: 6 + 4).
+template <int J>
+__device__ __forceinline__ void tc_pair_step(const uint32_t (&r)[32], const float* __restrict__ cn, float mult,
+                                             uint32_t mask, float& m1, float& m2) {
+    const float a = tc_pack_col<J>(fmaf(__uint_as_float(r[J]), mult, cn[J]), mask);
+    const float b = tc_pack_col<J + 1>(fmaf(__uint_as_float(r[J + 1]), mult, cn[J + 1]), mask);
+    const float lo = fminf(a, b), hi = fmaxf(a, b);
+    m2 = tc_min3(m2, fmaxf(m1, lo), hi);
+    m1 = fminf(m1, lo);
+}
+template <int... P>
+__device__ __forceinline__ void tc_two_smallest(const uint32_t (&r)[32], const float* __restrict__ cn, float mult,
+                                                uint32_t mask, float& m1, float& m2,
+                                                std::integer_sequence<int, P...>) {
+    (tc_pair_step<2 * P>(r, cn, mult, mask, m1, m2), ...);
 }
 // 32 consecutive fp32 columns of this thread's TMEM lane
 __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
@@ -116,76 +155,117 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
     return d;
 }
 
-// instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=128
-static constexpr uint32_t TC_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+// instruction descriptor: D=f32, A=B=f16 (format 0), both K-major, M=128, N=128
+static constexpr uint32_t TC_IDESC = (1u << 4) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
 
 #endif  // !DFX_EMU
 
 // ------------------------------------------------------------------ the kernel
 namespace tc {
 constexpr int TILE = 128;           // rows of A and of B per tile
-constexpr int KATOM = 64;           // bf16 elements per 128-byte swizzle row
+constexpr int KATOM = 64;           // fp16 elements per 128-byte swizzle row
 constexpr int ATOM_BYTES = TILE * KATOM * 2;  // 16 KB
-constexpr int NSTAGE = 8;
 constexpr int THREADS = 192;        // TMA warp + MMA warp + 4 epilogue warps
 constexpr int TMEM_COLS = 256;      // two 128-column accumulator buffers
+constexpr int MAX_RESIDENT_KATOMS = 4;  // query tile resident in shared memory up to 4 atoms (64 KB): FAST d <= 256, PRECISE d <= 128
+// Screening precision (NPL = planes per operand):
+//   FAST    NPL 1: fp16(x s); one MMA per k-step; error <= |q||c| (2^-10 + 2^-13)
+//   PRECISE NPL 2: hi = fp16(x s), lo = fp16(x s - hi); q.c ~= qh.ch + ql.ch + qh.cl, three MMAs per
+//           k-step; error <= |q||c| 2^-17 (the dropped ql.cl term is 2^-22, hi + lo carries 22 bits)
+// shared-memory plan (offsets inside the 1024-aligned dynamic block)
+//   resident A (NPL x katoms <= 4): A = NPL x katoms x 16 KB, then a ring of B stages of 16 KB
+//                          (FAST, d <= 128: 4 stages, 97 KB, two CTAs per SM; PRECISE: 8 stages)
+//   streamed A (larger d): a ring of 6 stages of (A atom + B atom) = 32 KB
 struct Smem {
-    // offsets inside the 1024-aligned dynamic shared memory block
-    static constexpr int A = 0;                                   // [plane hi/lo][katom] x 16 KB
-    static constexpr int B(int katoms) { return 2 * katoms * ATOM_BYTES; }
-    static constexpr int BARS(int katoms) { return B(katoms) + NSTAGE * ATOM_BYTES; }
-    static constexpr int total(int katoms) { return BARS(katoms) + 512 + 2 * TILE * 4; }
+    static constexpr bool resident(int katoms, int npl) { return npl * katoms <= MAX_RESIDENT_KATOMS; }
+    static constexpr int nstage(bool res, int npl) { return res ? (npl == 1 ? 4 : 8) : 6; }
+    static constexpr int stage_bytes(bool res) { return res ? ATOM_BYTES : 2 * ATOM_BYTES; }
+    static constexpr int RING(bool res, int katoms, int npl) { return res ? npl * katoms * ATOM_BYTES : 0; }
+    static constexpr int BARS(bool res, int katoms, int npl) {
+        return RING(res, katoms, npl) + nstage(res, npl) * stage_bytes(res);
+    }
+    static constexpr int total(bool res, int katoms, int npl) { return BARS(res, katoms, npl) + 512 + 2 * TILE * 4; }
 };
 }  // namespace tc
 
-#ifdef DFX_EMU
-// ---- CPU emulator stand-ins (tests/emu/): the screening kernel cannot be emulated instruction
-// by instruction, so its RESULT is restated: the same bf16 hi/lo split of both operands, the
-// same three partial products, fp32 accumulation (order not specified by the hardware either),
-// and the epilogue's packed (min, runner-up, arg-min) per 32 centroids.  Everything downstream
-// (group selection, exact canonical re-evaluation, the drivers) is the product code.
-struct __nv_bfloat16 { unsigned short x; };
-static inline float emu_bf16_rn(float v) {  // round to nearest even bf16, returned as fp32
-    uint32_t u;
-    memcpy(&u, &v, 4);
-    if ((u & 0x7f800000u) == 0x7f800000u) return v;
-    u += 0x7fffu + ((u >> 16) & 1u);
-    u &= 0xffff0000u;
-    float r;
-    memcpy(&r, &u, 4);
-    return r;
+// the power of two that brings a norm into [2^13, 2^14) (1 for a zero / non-finite norm; the
+// exponent is clamped to +-45, norms beyond 2^+-45 are outside what the screening supports)
+__host__ __device__ __forceinline__ float dfx_pow2_scale(float nrm) {
+    if (!(nrm > 0.f) || !(nrm < 3.0e38f)) return 1.f;
+    int e;
+    frexpf(nrm, &e);  // nrm = m 2^e, m in [0.5, 1)
+    e = e < -45 ? -45 : (e > 45 ? 45 : e);
+    return ldexpf(1.f, 14 - e);
 }
-// "planes" hold a padded fp32 copy in the emulator build (same byte size as the two bf16 planes)
-__global__ void split_bf16_kernel(const float* __restrict__ x, int64_t n, int64_t n_pad, int d,
-                                  __nv_bfloat16* __restrict__ out) {
-    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n_pad * d) return;
-    reinterpret_cast<float*>(out)[t] = (t / d < n) ? x[t] : 0.f;
-}
-static void emu_tc_screen(const float* q, int64_t nq, const float* c, int64_t nlist, int64_t nl_pad, int d,
-                          const float* cnorm, int metric, float* gmin, float* gmin2, uint8_t* gargc, int ng) {
-    const float big = 3.0e38f;
-    std::vector<float> ch((size_t)nl_pad * d), cl((size_t)nl_pad * d), qh(d), ql(d);
-    for (size_t i = 0; i < ch.size(); i++) {
-        ch[i] = emu_bf16_rn(c[i]);
-        cl[i] = emu_bf16_rn(c[i] - ch[i]);
-    }
-    for (int64_t row = 0; row < nq; row++) {
-        for (int k = 0; k < d; k++) {
-            qh[k] = emu_bf16_rn(q[row * d + k]);
-            ql[k] = emu_bf16_rn(q[row * d + k] - qh[k]);
+
+// fp32 rows -> fp16 rows scaled by a power of two, rows >= n zero filled; one warp per row.
+//   row_scaled != 0 (queries): the row is scaled so that its norm lands in [2^13, 2^14) and
+//       mult[row] = factor / (row scale * table_scale) -- what the screening epilogue multiplies
+//       the accumulator with (factor = -2 for L2, -1 for inner product; all powers of two, exact);
+//   row_scaled == 0 (a centroid table / the rows of a FLAT index): every row times table_scale.
+// Elements more than 2^28 below the row norm fall into fp16's subnormal range and lose relative
+// (not absolute) precision: an error of at most 2^-39 of the norm, far inside screen_tol.
+// npl == 2 also writes the residual plane lo = fp16(x s - hi) at out + n_pad * d.
+__global__ void __launch_bounds__(256)
+f16_rows_kernel(const float* __restrict__ x, int64_t n, int64_t n_pad, int d, int row_scaled, float table_scale,
+                float factor, int npl, __half* __restrict__ out, float* __restrict__ mult, float* __restrict__ norm2) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= n_pad) return;
+    const bool real = row < n;
+    float scale = table_scale;
+    if (row_scaled) {
+        float part = 0.f;
+        if (real)
+            for (int k = lane; k < d; k += 32) {
+                const float v = x[row * d + k];
+                part = __fmaf_rn(v, v, part);
+            }
+        const float n2 = dfx_warp_butterfly(part);
+        scale = dfx_pow2_scale(sqrtf(n2));
+        if (lane == 0) {
+            mult[row] = factor / (scale * table_scale);
+            if (norm2) norm2[row] = n2;
         }
+    }
+    for (int k = lane; k < d; k += 32) {
+        const float v = real ? x[row * d + k] * scale : 0.f;
+        const __half hi = __float2half_rn(v);
+        out[row * d + k] = hi;
+        if (npl == 2) out[n_pad * d + row * d + k] = __float2half_rn(v - __half2float(hi));
+    }
+}
+
+#ifdef DFX_EMU
+// ---- CPU emulator stand-in (tests/emu/): the screening kernel cannot be emulated instruction
+// by instruction, so its RESULT is restated: the fp16 operands the product code prepared
+// (f16_rows_kernel), fp32 accumulation (order not specified by the hardware either), the
+// epilogue's ranking value fma(acc, mult[row], cn) and its packed (min, runner-up, arg-min) per
+// 32 centroids.  Everything downstream (group selection, exact canonical re-evaluation, the
+// overflow fallback, the drivers) is the product code.
+static void emu_tc_screen(const __half* qh, const float* qmult, int64_t nq, int64_t nq_pad, const __half* ch,
+                          int64_t nlist, int64_t nl_pad, int d, int npl, const float* cnorm, int metric, float* gmin,
+                          float* gmin2, uint8_t* gargc, int ng) {
+    const float big = 3.0e38f;
+    std::vector<float> cf((size_t)npl * nl_pad * d), qf((size_t)npl * d);
+    for (size_t i = 0; i < cf.size(); i++) cf[i] = __half2float(ch[i]);
+    for (int64_t row = 0; row < nq; row++) {
+        for (int pl = 0; pl < npl; pl++)
+            for (int k = 0; k < d; k++) qf[(size_t)pl * d + k] = __half2float(qh[(size_t)pl * nq_pad * d + row * d + k]);
         for (int g = 0; g < ng; g++) {
             float m1 = big, m2 = big;
             for (int j = 0; j < 32; j++) {
                 const int64_t col = (int64_t)g * 32 + j;
-                float ip = 0.f;
-                const float* h = &ch[(size_t)col * d];
-                const float* l = &cl[(size_t)col * d];
-                for (int k = 0; k < d; k++) ip += qh[k] * h[k] + ql[k] * h[k] + qh[k] * l[k];
+                float acc = 0.f;
+                const float* h = &cf[(size_t)col * d];
+                for (int k = 0; k < d; k++) acc += qf[k] * h[k];
+                if (npl == 2) {
+                    const float* l = &cf[(size_t)nl_pad * d + (size_t)col * d];
+                    for (int k = 0; k < d; k++) acc += qf[d + k] * h[k] + qf[k] * l[k];
+                }
                 float cn = big;
                 if (col < nlist) cn = (metric == DFX_METRIC_L2) ? cnorm[col] : 0.f;
-                const float v = (metric == DFX_METRIC_IP) ? (cn - ip) : fmaf(-2.f, ip, cn);
+                const float v = fmaf(acc, qmult[row], cn);
                 uint32_t u;
                 memcpy(&u, &v, 4);
                 u = (u & ~31u) | (uint32_t)j;
@@ -203,28 +283,37 @@ static void emu_tc_screen(const float* q, int64_t nq, const float* c, int64_t nl
     }
 }
 #else
-// tmQ: bf16 [2*nq_pad, d]  (rows [0,nq_pad) = hi plane, [nq_pad, 2 nq_pad) = lo plane)
-// tmC: bf16 [2*nl_pad, d]
-// gmin: float [nq][ng], ng = nl_pad/32
-template <int KATOMS, int METRIC>
-__global__ void __launch_bounds__(tc::THREADS, 1)
+// tmQ: fp16 [NPL * nq_pad, d] (scaled query rows; NPL == 2: hi plane then lo plane), tmC: fp16
+// [NPL * nl_pad, d] (scaled table rows), d = 64 KATOMS
+// qmult: float [nq_pad], the per-row multiplier of the accumulator (f16_rows_kernel)
+// gmin / gmin2: float [nq][ng], gargc: u8 [nq][ng], ng = nl_pad/32
+// KT: d / 64 at compile time for the resident shapes (1, 2, 4); 0 = streamed, k-atoms at run time
+template <int KT, int METRIC, int NPL>
+__global__ void __launch_bounds__(tc::THREADS, (KT != 0 && NPL == 1) ? 2 : 1)
 tc_coarse_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmC, int nq,
-                 int nq_pad, int nlist, int nl_pad, const float* __restrict__ cnorm, int metric, int ctiles_per_cta,
-                 float* __restrict__ gmin, float* __restrict__ gmin2, uint8_t* __restrict__ gargc, int ng) {
+                 int nq_pad, int nlist, int nl_pad, int katoms_rt, const float* __restrict__ cnorm,
+                 const float* __restrict__ qmult, int ctiles_per_cta, float* __restrict__ gmin,
+                 float* __restrict__ gmin2, uint8_t* __restrict__ gargc, int ng) {
     using namespace tc;
+    constexpr bool RES = KT != 0;
+    const int KATOMS = KT ? KT : katoms_rt;
+    constexpr int NSTAGE = Smem::nstage(RES, NPL);
+    constexpr int STAGE_BYTES = Smem::stage_bytes(RES);
+    // operand pairs accumulated per k-atom: FAST (qh, ch); PRECISE (qh, ch), (ql, ch), (qh, cl)
+    constexpr int NCOMBO = NPL == 1 ? 1 : 3;
     extern __shared__ unsigned char smem_raw_tc[];
     unsigned char* smem = reinterpret_cast<unsigned char*>(
         (reinterpret_cast<uintptr_t>(smem_raw_tc) + 1023) & ~(uintptr_t)1023);  // SWIZZLE_128B atoms
-    unsigned char* sA = smem + Smem::A;
-    unsigned char* sB = smem + Smem::B(KATOMS);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Smem::BARS(KATOMS));
+    unsigned char* sA = smem;                            // RES: [plane][katom] x 16 KB
+    unsigned char* sR = smem + Smem::RING(RES, KATOMS, NPL);  // ring: B atom (RES) or A atom + B atom
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Smem::BARS(RES, KATOMS, NPL));
     uint64_t* full = bars;                 // [NSTAGE]
     uint64_t* empty = bars + NSTAGE;       // [NSTAGE]
     uint64_t* a_full = bars + 2 * NSTAGE;  // [1]
     uint64_t* t_full = a_full + 1;         // [2]
     uint64_t* t_empty = t_full + 2;        // [2]
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(t_empty + 2);
-    float* s_cn = reinterpret_cast<float*>(smem + Smem::BARS(KATOMS) + 512);  // [2][TILE]
+    float* s_cn = reinterpret_cast<float*>(smem + Smem::BARS(RES, KATOMS, NPL) + 512);  // [2][TILE]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int qt = blockIdx.y;
@@ -253,24 +342,33 @@ tc_coarse_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
 
-    constexpr int STAGES_PER_TILE = 2 * KATOMS;  // ch atoms then cl atoms
-
     if (warp == 0) {
         // ===================== TMA producer =====================
+        // RES: per tile, the B atoms of the hi plane then (PRECISE) of the lo plane.
+        // streamed: per tile and k-atom, the (A atom, B atom) pair of every combo.
         if (lane == 0) {
-            mbar_expect_tx(a_full, 2 * KATOMS * ATOM_BYTES);
-            for (int pl = 0; pl < 2; pl++)
-                for (int ka = 0; ka < KATOMS; ka++)
-                    tma_load_2d(sA + (pl * KATOMS + ka) * ATOM_BYTES, &tmQ, a_full, ka * KATOM,
-                                pl * nq_pad + qt * TILE);
+            if (RES) {
+                mbar_expect_tx(a_full, NPL * KATOMS * ATOM_BYTES);
+                for (int pl = 0; pl < NPL; pl++)
+                    for (int ka = 0; ka < KATOMS; ka++)
+                        tma_load_2d(sA + (pl * KATOMS + ka) * ATOM_BYTES, &tmQ, a_full, ka * KATOM,
+                                    pl * nq_pad + qt * TILE);
+            }
             int stage = 0, phase = 0;
             for (int t = 0; t < ntiles; t++) {
                 const int crow = (ct0 + t) * TILE;
-                for (int s = 0; s < STAGES_PER_TILE; s++) {
-                    const int pl = s / KATOMS, ka = s % KATOMS;
+                // RES: c = B plane; streamed: c = combo
+                for (int c = 0; c < (RES ? NPL : NCOMBO); c++)
+                for (int ka = 0; ka < KATOMS; ka++) {
                     mbar_wait(&empty[stage], phase ^ 1);
-                    mbar_expect_tx(&full[stage], ATOM_BYTES);
-                    tma_load_2d(sB + stage * ATOM_BYTES, &tmC, &full[stage], ka * KATOM, pl * nl_pad + crow);
+                    mbar_expect_tx(&full[stage], STAGE_BYTES);
+                    unsigned char* dst = sR + stage * STAGE_BYTES;
+                    if (!RES) {
+                        tma_load_2d(dst, &tmQ, &full[stage], ka * KATOM, (c == 1 ? nq_pad : 0) + qt * TILE);
+                        dst += ATOM_BYTES;
+                    }
+                    const int bpl = RES ? c : (c == 2 ? 1 : 0);
+                    tma_load_2d(dst, &tmC, &full[stage], ka * KATOM, bpl * nl_pad + crow);
                     if (++stage == NSTAGE) {
                         stage = 0;
                         phase ^= 1;
@@ -281,31 +379,36 @@ tc_coarse_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     } else if (warp == 1) {
         // ===================== MMA issuer (one thread) =====================
         if (lane == 0) {
-            mbar_wait(a_full, 0);
-            tc_fence_after();
+            if (RES) {
+                mbar_wait(a_full, 0);
+                tc_fence_after();
+            }
             int stage = 0, phase = 0;
             const uint32_t a_base = smem_u32(sA);
-            const uint32_t b_base = smem_u32(sB);
+            const uint32_t r_base = smem_u32(sR);
             for (int t = 0; t < ntiles; t++) {
                 const int buf = t & 1;
                 mbar_wait(&t_empty[buf], ((t >> 1) & 1) ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + buf * TILE;
-                for (int s = 0; s < STAGES_PER_TILE; s++) {
-                    const int pl = s / KATOMS, ka = s % KATOMS;
+#pragma unroll
+                for (int c = 0; c < (RES ? NPL : NCOMBO); c++)
+#pragma unroll
+                for (int ka = 0; ka < KATOMS; ka++) {
                     mbar_wait(&full[stage], phase);
                     tc_fence_after();
-                    const uint32_t b_addr = b_base + stage * ATOM_BYTES;
-                    const uint32_t ah_addr = a_base + (0 * KATOMS + ka) * ATOM_BYTES;
-                    const uint32_t al_addr = a_base + (1 * KATOMS + ka) * ATOM_BYTES;
+                    const uint32_t st_addr = r_base + stage * STAGE_BYTES;
+                    const uint32_t b_addr = RES ? st_addr : st_addr + ATOM_BYTES;
+                    const uint32_t ah_addr = RES ? a_base + ka * ATOM_BYTES : st_addr;
+                    const uint32_t al_addr = a_base + (KATOMS + ka) * ATOM_BYTES;  // RES && NPL == 2 only
 #pragma unroll
-                    for (int kk = 0; kk < KATOM / 16; kk++) {  // UMMA_K = 16 bf16 = 32 bytes
+                    for (int kk = 0; kk < KATOM / 16; kk++) {  // UMMA_K = 16 fp16 = 32 bytes
                         const uint64_t bd = make_kmajor_sw128_desc(b_addr + kk * 32);
-                        // qh . (ch | cl)
-                        tc_mma_bf16(d_tmem, make_kmajor_sw128_desc(ah_addr + kk * 32), bd, TC_IDESC,
-                                    (s > 0 || kk > 0) ? 1u : 0u);
-                        // ql . ch
-                        if (pl == 0) tc_mma_bf16(d_tmem, make_kmajor_sw128_desc(al_addr + kk * 32), bd, TC_IDESC, 1u);
+                        tc_mma_f16(d_tmem, make_kmajor_sw128_desc(ah_addr + kk * 32), bd, TC_IDESC,
+                                   (c > 0 || ka > 0 || kk > 0) ? 1u : 0u);
+                        // resident PRECISE: the hi-plane B stage also takes ql . ch
+                        if (RES && NPL == 2 && c == 0)
+                            tc_mma_f16(d_tmem, make_kmajor_sw128_desc(al_addr + kk * 32), bd, TC_IDESC, 1u);
                     }
                     tc_commit(&empty[stage]);  // frees the stage once these MMAs have read it
                     if (++stage == NSTAGE) {
@@ -318,15 +421,19 @@ tc_coarse_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         }
     } else {
         // ===================== epilogue: TMEM -> per-group (min, runner-up, argmin) =============
-        // The epilogue is bound by the half-rate ALU pipe, so it is kept to 3 FMNMX + 1 LOP3 per
-        // element: the column index (0..31) replaces the 5 low mantissa bits of the screening
-        // value (a 2^-18 relative perturbation, far below the screening tolerance), which makes
-        // the arg-min fall out of the minimum itself; the runner-up is min(m2, max(m1, v)).
+        // The epilogue is bound by the half-rate ALU pipe (and, with one MMA per k-step, it is the
+        // longest stage of the kernel), so it is kept to 3.5 ALU instructions per element
+        // (tc_two_smallest): the column index (0..31) replaces the 5 low mantissa bits of the
+        // screening value (a 2^-18 relative perturbation, inside the screening tolerance), which
+        // makes the arg-min fall out of the minimum itself.
         const int quad = warp & 3;             // TMEM lane quadrant this warp may access
         const int row = quad * 32 + lane;      // query row inside the tile == TMEM lane
         const int64_t grow = (int64_t)qt * TILE + row;
         const int et = threadIdx.x - 64;       // 0..127
         const float big = 3.0e38f;             // out-of-range columns: finite, never selected
+        const float mult = qmult[grow];        // padded rows carry a multiplier too
+        uint32_t idx_mask;                     // ~31 in a REGISTER: (v & mask) | j is then one LOP3
+        asm volatile("mov.u32 %0, 0xffffffe0;" : "=r"(idx_mask));
         for (int t = 0; t < ntiles; t++) {
             const int buf = t & 1;
             const int col0 = (ct0 + t) * TILE;
@@ -346,15 +453,8 @@ tc_coarse_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                 uint32_t r[32];
                 tc_ld32(tmem_base + buf * TILE + ch * 32 + ((uint32_t)(quad * 32) << 16), r);
                 float m1 = big, m2 = big;
-#pragma unroll
-                for (int j = 0; j < 32; j++) {
-                    const float ip = __uint_as_float(r[j]);
-                    const float cn = s_cn[buf * TILE + ch * 32 + j];
-                    const float v = (METRIC == DFX_METRIC_IP) ? (cn - ip) : fmaf(-2.f, ip, cn);
-                    const float vj = __uint_as_float((__float_as_uint(v) & ~31u) | (uint32_t)j);
-                    m2 = fminf(m2, fmaxf(m1, vj));
-                    m1 = fminf(m1, vj);
-                }
+                tc_two_smallest(r, s_cn + buf * TILE + ch * 32, mult, idx_mask, m1, m2,
+                                std::make_integer_sequence<int, 16>{});
                 gm[ch] = m1;
                 gm2[ch] = m2;
                 ga |= (__float_as_uint(m1) & 31u) << (8 * ch);
@@ -377,21 +477,6 @@ tc_coarse_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         tc_dealloc(tmem_base, TMEM_COLS);
     }
 }
-
-// ------------------------------------------------------------------ helpers around it
-// fp32 [n, d] -> bf16 hi/lo planes [2][n_pad][d] (rows >= n zero filled)
-__global__ void split_bf16_kernel(const float* __restrict__ x, int64_t n, int64_t n_pad, int d,
-                                  __nv_bfloat16* __restrict__ out) {
-    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n_pad * d) return;
-    int64_t i = t / d;
-    float v = (i < n) ? x[t] : 0.f;
-    __nv_bfloat16 hi = __float2bfloat16_rn(v);
-    __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
-    out[t] = hi;
-    out[n_pad * d + t] = lo;
-}
-
 #endif  // DFX_EMU
 
 // the G smallest group minima of a row, G <= 8: one warp per row, G rounds of warp arg-min
@@ -429,10 +514,47 @@ __global__ void topg_small_kernel(const float* __restrict__ gmin, int64_t nq, in
 // has approx(c) <= t + tol; inside its group it is either the arg-min column or has
 // approx(c) >= gmin2(group).  So a group is expanded to all 32 columns only if
 // gmin2 <= t + tol, otherwise its arg-min column is the only candidate.
-__device__ __forceinline__ float screen_tol(float qn2, float cmax2) {
-    // bf16-split error ~1e-5 |q||c|, plus the 2^-18 |v| perturbation of the packed column index
-    // (|v| <= |c|^2 + 2|q||c|); both with a wide margin
-    return 1e-4f * (sqrtf(qn2 * cmax2) + cmax2) + 1e-30f;
+//
+// Screening error, s = |q| max|c| (Cauchy-Schwarz bounds sum |q_k c_k| by it):
+//   FAST (fp16 operands): every product carries two relative roundings of at most 2^-11
+//     (2^-10 + 2^-22 together), the fp32 accumulation of the d products at most d 2^-24:
+//       |q.c - screen| <= s (2^-10 + 2^-22 + d 2^-24)
+//   PRECISE (hi + lo planes, three partial products): hi + lo represents an operand to 2^-22, the
+//     dropped ql.cl term is 2^-22, 3d products are accumulated:
+//       |q.c - screen| <= s (3 2^-22 + 3 d 2^-24)
+// The L2 ranking value |c|^2 - 2 q.c doubles it and the tolerance must be twice the error of a
+// value (threshold and candidate are both approximations): tol = 4 err (+5 % slack).  The packed
+// column index perturbs a value by 2^-18 |v|, |v| <= max|c|^2 + 2 s: the 1e-5 term.
+static float screen_tol_rel(int d, bool fast) {
+    const double err = fast ? (1.0 / 1024 + 1.0 / 4194304 + d / 16777216.0) : (3.0 / 4194304 + 3.0 * d / 16777216.0);
+    return (float)(4.2 * err);
+}
+__device__ __forceinline__ float screen_tol(float qn2, float cmax2, float rel) {
+    const float s = sqrtf(qn2 * cmax2);
+    return rel * s + 1e-5f * (cmax2 + 2.f * s) + 1e-30f;
+}
+// "the selected groups may not be all that matter": the G-th (last) selected group is itself
+// within the tolerance, so an unselected group could be too -> the row is re-done exactly
+__device__ __forceinline__ bool screen_overflow(const int32_t* __restrict__ groups, int64_t row, int G, int ng,
+                                                const float* __restrict__ gmin, float thr) {
+    if (G >= ng) return false;  // every group is selected
+    const int gl = groups[row * G + G - 1];
+    return gl >= 0 && gmin[row * ng + gl] <= thr;
+}
+// ovf = [overflow rows, rows that the FAST tolerance would overflow (counted by PRECISE launches
+// for the AUTO mode), row list ...].  t = the nprobe-th smallest group minimum (inf: no pruning).
+struct ScreenTol {
+    float rel;       // of this launch's precision
+    float rel_fast;  // > 0: also count the rows FAST would overflow
+};
+__device__ __forceinline__ float screen_threshold(const int32_t* __restrict__ groups, int64_t row, int G, int ng,
+                                                  const float* __restrict__ gmin, float t, float qn2, float cmax2,
+                                                  ScreenTol tol, int32_t* __restrict__ ovf) {
+    const float thr = t + screen_tol(qn2, cmax2, tol.rel);
+    if (screen_overflow(groups, row, G, ng, gmin, thr)) ovf[2 + atomicAdd(&ovf[0], 1)] = (int32_t)row;
+    if (tol.rel_fast > 0.f && screen_overflow(groups, row, G, ng, gmin, t + screen_tol(qn2, cmax2, tol.rel_fast)))
+        atomicAdd(&ovf[1], 1);
+    return thr;
 }
 
 // The G (<= 32) smallest group minima of a row, ascending by (value, group): one warp per row.
@@ -543,9 +665,9 @@ __global__ void __launch_bounds__(128)
 rerank_kernel(const float* __restrict__ Q, int d, const float* __restrict__ cent, const float* __restrict__ cnorm,
               int64_t nlist, int metric, const int32_t* __restrict__ groups, int G, int nprobe,
               const float* __restrict__ gmin, const float* __restrict__ gmin2, const uint8_t* __restrict__ gargc,
-              int ng, float cmax2, uint64_t* __restrict__ out, int32_t* __restrict__ assign,
+              int ng, float cmax2, ScreenTol tol, uint64_t* __restrict__ out, int32_t* __restrict__ assign,
               const int32_t* __restrict__ rows, const int32_t* __restrict__ nrows_dev, int64_t nrows,
-              int32_t* __restrict__ keys) {
+              int32_t* __restrict__ keys, int32_t* __restrict__ ovf) {
     DFX_DYN_SMEM(unsigned char, rr_smem, 16);
     float* s_q = reinterpret_cast<float*>(rr_smem);
     uint64_t* s_c = reinterpret_cast<uint64_t*>(rr_smem + ((size_t)d * 4 + 15) / 16 * 16);  // MODE 2
@@ -565,7 +687,9 @@ rerank_kernel(const float* __restrict__ Q, int d, const float* __restrict__ cent
             for (int i = 0; i < d; i++) qn2 += s_q[i] * s_q[i];
             // the bound needs nprobe distinct groups: with fewer groups than probes nothing is pruned
             const int gk = (nprobe <= G) ? groups[row * G + nprobe - 1] : -1;
-            s_thr = (gk >= 0 ? gmin[row * ng + gk] : __int_as_float(0x7f800000)) + screen_tol(qn2, cmax2);
+            // (more near-ties than selected groups: the row is also queued for tc_exact_rows_kernel)
+            s_thr = screen_threshold(groups, row, G, ng, gmin,
+                                     gk >= 0 ? gmin[row * ng + gk] : __int_as_float(0x7f800000), qn2, cmax2, tol, ovf);
         }
         __syncthreads();
         const float thr = s_thr;
@@ -640,7 +764,8 @@ __global__ void __launch_bounds__(RR2_WARPS * 32)
 rerank2_kernel(const float* __restrict__ Q, int d, const float* __restrict__ cent, const float* __restrict__ cnorm,
                int64_t nlist, int metric, const int32_t* __restrict__ groups, int G, int nprobe,
                const float* __restrict__ gmin, const float* __restrict__ gmin2, const uint8_t* __restrict__ gargc,
-               int ng, float cmax2, int64_t nrows, int32_t* __restrict__ keys) {
+               int ng, float cmax2, ScreenTol tol, int64_t nrows, int32_t* __restrict__ keys,
+               int32_t* __restrict__ ovf) {
     DFX_DYN_SMEM(unsigned char, rr2_smem, 16);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t row = (int64_t)blockIdx.x * RR2_WARPS + warp;
@@ -657,7 +782,11 @@ rerank2_kernel(const float* __restrict__ Q, int d, const float* __restrict__ cen
     const float qn2 = dfx_warp_butterfly(part);
     __syncwarp();
     const int gk = (nprobe <= G) ? groups[row * G + nprobe - 1] : -1;
-    const float thr = (gk >= 0 ? gmin[row * ng + gk] : __int_as_float(0x7f800000)) + screen_tol(qn2, cmax2);
+    float thr = 0.f;
+    if (lane == 0)
+        thr = screen_threshold(groups, row, G, ng, gmin, gk >= 0 ? gmin[row * ng + gk] : __int_as_float(0x7f800000),
+                               qn2, cmax2, tol, ovf);
+    thr = __shfl_sync(0xffffffffu, thr, 0);
     // ---- candidate list: one entry for a live group's arg-min column, 32 for an expanded group
     int cnt = 0;
     for (int g0 = 0; g0 < G; g0 += 32) {
@@ -719,14 +848,18 @@ rerank2_kernel(const float* __restrict__ Q, int d, const float* __restrict__ cen
 // for the exact evaluation above.
 __global__ void assign_resolve_kernel(const float* __restrict__ qnorm2, const int32_t* __restrict__ groups,
                                       const float* __restrict__ gmin, const float* __restrict__ gmin2,
-                                      const uint8_t* __restrict__ gargc, int ng, float cmax2, int64_t n,
-                                      int32_t* __restrict__ assign, int32_t* __restrict__ amb_rows,
-                                      int32_t* __restrict__ amb_count) {
+                                      const uint8_t* __restrict__ gargc, int ng, int G, float cmax2, float tol_rel,
+                                      float tol_rel_fast, int64_t n, int32_t* __restrict__ assign,
+                                      int32_t* __restrict__ amb_rows, int32_t* __restrict__ amb_count,
+                                      int32_t* __restrict__ ovf) {
     const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= n) return;
-    const int g0 = groups[row * 2 + 0], g1 = groups[row * 2 + 1];
+    const int g0 = groups[row * G + 0], g1 = (G > 1) ? groups[row * G + 1] : -1;
     const int64_t o0 = row * ng + g0;
-    const float thr = gmin[o0] + screen_tol(qnorm2[row], cmax2);
+    const float thr = gmin[o0] + screen_tol(qnorm2[row], cmax2, tol_rel);
+    if (tol_rel_fast > 0.f &&
+        screen_overflow(groups, row, G, ng, gmin, gmin[o0] + screen_tol(qnorm2[row], cmax2, tol_rel_fast)))
+        atomicAdd(&ovf[1], 1);  // AUTO mode statistic: FAST would send this row to the exact fallback
     const bool clear = gmin2[o0] > thr && (g1 < 0 || gmin[row * ng + g1] > thr);
     if (clear) {
         assign[row] = g0 * 32 + (int)gargc[o0];
@@ -734,6 +867,60 @@ __global__ void assign_resolve_kernel(const float* __restrict__ qnorm2, const in
         assign[row] = -1;
         amb_rows[atomicAdd(amb_count, 1)] = (int32_t)row;
     }
+}
+
+// ---- exact fallback for the rows the decide stage flagged (screen_overflow): the K smallest
+// composites over ALL columns, canonical values computed on the fly (seq-k FMA, the same chain as
+// rerank_kernel), selected by the radix select of dfx_select.cuh.  Rare by construction (more than
+// `margin` group minima within the tolerance: duplicate centroids / duplicate rows); slow but exact.
+struct ExactLoader {
+    const float* Q;
+    const float* X;
+    const float* xnorm;
+    int d, metric;
+    __device__ __forceinline__ uint64_t operator()(int64_t row, int e) const {
+        const float* q = Q + row * d;
+        const float* x = X + (int64_t)e * d;
+        float acc = 0.f;
+        for (int k = 0; k < d; k++) acc = __fmaf_rn(q[k], x[k], acc);
+        const float v = (metric == DFX_METRIC_IP) ? -acc : __fmaf_rn(-2.f, acc, xnorm[e]);
+        return dfx_comp(v, (uint32_t)e);
+    }
+};
+struct ExactWriter {  // mode 2: keys[row][K]; mode 1: assign[row]; mode 0: out[row][K] composites
+    int mode, K;
+    int32_t* keys;
+    int32_t* assign;
+    uint64_t* out;
+    __device__ __forceinline__ void operator()(int64_t row, int j, uint64_t c) const {
+        const int32_t col = (c == DFX_COMP_NONE) ? -1 : (int32_t)(uint32_t)c;
+        if (mode == 2) keys[row * K + j] = col;
+        else if (mode == 1) assign[row] = col;
+        else out[row * K + j] = c;
+    }
+};
+__global__ void __launch_bounds__(256)
+tc_exact_rows_kernel(ExactLoader ld, ExactWriter wr, const int32_t* __restrict__ ovf, int n, int k, int P,
+                     int sort_cap) {
+    DFX_DYN_SMEM(unsigned char, ex_smem, 16);
+    const int count = ovf[0];
+    for (int b = blockIdx.x; b < count; b += gridDim.x) {
+        dfx_select_row<256>(ld, wr, (int64_t)ovf[2 + b], n, k, P, sort_cap, reinterpret_cast<uint64_t*>(ex_smem));
+        __syncthreads();
+    }
+}
+// mode / K as in ExactWriter; Q rows are indexed by the values in ovf (chunk-relative)
+static void launch_exact_rows(const float* Q, const float* X, const float* xnorm, int64_t ncols, int d, int metric,
+                              const int32_t* ovf, int64_t nrows, int mode, int K, int32_t* keys, int32_t* assign,
+                              uint64_t* out, cudaStream_t st) {
+    DFX_REQUIRE(K >= 1 && K <= 4096 && ncols < (1ll << 31), "exact fallback: bad K / column count");
+    const int sort_cap = 2048, n = (int)ncols;
+    const int base = (n <= sort_cap) ? (n > K ? n : K) : K;
+    const int P = dfx_next_pow2(base < 2 ? 2 : base);
+    ExactLoader ld{Q, X, xnorm, d, metric};
+    ExactWriter wr{mode, K, keys, assign, out};
+    const unsigned grid = (unsigned)std::min<int64_t>(nrows, 2 * 148);
+    DFX_LAUNCH(tc_exact_rows_kernel, grid, 256, (size_t)P * 8, st, ld, wr, ovf, n, K, P, sort_cap);
 }
 
 __global__ void max_reduce_kernel(const float* __restrict__ x, int64_t n, float* __restrict__ out) {
@@ -762,13 +949,13 @@ static PFN_encodeTiled get_encode_fn() {
     return fn;
 }
 
-// bf16 matrix [rows, d] row-major, box = 128 rows x 64 columns, 128-byte swizzle
+// fp16 matrix [rows, d] row-major, box = 128 rows x 64 columns, 128-byte swizzle
 static void make_tmap(CUtensorMap* tm, const void* base, int64_t rows, int d) {
     cuuint64_t gdim[2] = {(cuuint64_t)d, (cuuint64_t)rows};
     cuuint64_t gstr[1] = {(cuuint64_t)d * 2};
     cuuint32_t box[2] = {(cuuint32_t)tc::KATOM, (cuuint32_t)tc::TILE};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = get_encode_fn()(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box,
+    CUresult r = get_encode_fn()(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), gdim, gstr, box,
                                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     DFX_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
@@ -776,7 +963,8 @@ static void make_tmap(CUtensorMap* tm, const void* base, int64_t rows, int d) {
 
 #endif  // !DFX_EMU
 
-bool dfx_tc_supported(int d) { return d == 64 || d == 128; }
+// d = a whole number of 64-element k-atoms (d <= 256: query tile resident; above: streamed)
+bool dfx_tc_supported(int d) { return d >= 64 && d % 64 == 0 && d <= 2048; }
 
 // max |c|^2 of a centroid table (for the screening tolerance), synchronises
 static float max_norm2(dfx_index* idx, const float* cnorm, int64_t nlist, cudaStream_t st) {
@@ -789,43 +977,119 @@ static float max_norm2(dfx_index* idx, const float* cnorm, int64_t nlist, cudaSt
     return h;
 }
 
-// (re)build the bf16 planes of the centroids; call after training / import
+// fp16 copy of a table (centroids / FLAT rows), npl planes, scaled so that the largest row norm
+// lands in [2^13, 2^14); returns the scale
+static float tc_prepare_table(const float* x, int64_t n, int d, float cmax2, int npl, DevBuf& out, cudaStream_t st) {
+    const int64_t n_pad = dfx_ceil_div(n, tc::TILE) * tc::TILE;
+    out.reserve((size_t)npl * n_pad * d * 2);
+    const float scale = dfx_pow2_scale(sqrtf(cmax2));
+    DFX_LAUNCH(f16_rows_kernel, (unsigned)dfx_ceil_div(n_pad, 8), 256, 0, st, x, n, n_pad, d, 0, scale, 0.f, npl,
+               out.as<__half>(), (float*)nullptr, (float*)nullptr);
+    return scale;
+}
+
+// (re)build the fp16 copy of the centroids (both planes: either precision can use it); call after
+// training / import
 void dfx_tc_prepare_centroids(dfx_index* idx, cudaStream_t st) {
     const int d = idx->cfg.d;
     if (!dfx_tc_supported(d)) return;
     const int64_t nlist = idx->cfg.nlist;
-    const int64_t nl_pad = dfx_ceil_div(nlist, tc::TILE) * tc::TILE;
-    idx->tc_cent.reserve((size_t)2 * nl_pad * d * 2);
-    DFX_LAUNCH(split_bf16_kernel, (unsigned)dfx_ceil_div(nl_pad * d, 256), 256, 0, st, idx->centroids.as<float>(),
-               nlist, nl_pad, d, idx->tc_cent.as<__nv_bfloat16>());
     idx->tc_cmax2 = max_norm2(idx, idx->cnorm.as<float>(), nlist, st);
+    idx->tc_cscale = tc_prepare_table(idx->centroids.as<float>(), nlist, d, idx->tc_cmax2, 2, idx->tc_cent, st);
+    idx->tc_cent_npl = 2;
     idx->tc_ready = true;
+    if (idx->tc_mode == 0) idx->tc_fast = false;  // AUTO: a new table starts PRECISE
+    idx->tc_stat_pending = false;
 }
 
-// screening pass: gmin[nq][ng] for a batch of rows against any centroid table with bf16 planes
-static void tc_screen(dfx_index* idx, int d, const float* d_x, int64_t nq, const void* cent_planes,
-                      const float* cnorm, int64_t nlist, int metric, float* gmin, float* gmin2, uint8_t* gargc,
-                      cudaStream_t st) {
+// ---- AUTO precision: statistics of a past launch come back through pinned memory, no sync
+static bool tc_stream_capturing(cudaStream_t st) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cs) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return cs != cudaStreamCaptureStatusNone;
+}
+// AUTO rule: PRECISE -> FAST when at most 1/256 of a launch's rows would overflow under FAST's
+// tolerance; FAST -> PRECISE when more than 1/64 of a launch's rows overflowed.  Either way the
+// results are exact; only the cost moves.  A switch bumps `generation` (captured graphs are stale).
+static void tc_auto_update(dfx_index* idx, bool was_fast, int64_t rows, int64_t overflowed, int64_t fast_would) {
+    if (idx->tc_mode != 0 || rows <= 0) return;
+    bool fast = idx->tc_fast;
+    if (was_fast && overflowed * 64 > rows) fast = false;
+    else if (!was_fast && fast_would * 256 <= rows) fast = true;
+    if (fast != idx->tc_fast) {
+        idx->tc_fast = fast;
+        idx->generation++;
+    }
+}
+static void tc_stats_poll(dfx_index* idx) {  // before choosing the precision of a launch
+    if (!idx->tc_stat_pending) return;
+    if (cudaEventQuery(idx->tc_stat_ev) != cudaSuccess) {
+        cudaGetLastError();  // not ready yet: keep the current precision
+        return;
+    }
+    idx->tc_stat_pending = false;
+    idx->tc_last_rows = idx->tc_stat_rows;
+    idx->tc_last_overflow = idx->tc_stat_h[0];
+    idx->tc_last_fast_would = idx->tc_stat_h[1];
+    tc_auto_update(idx, idx->tc_stat_fast, idx->tc_stat_rows, idx->tc_stat_h[0], idx->tc_stat_h[1]);
+}
+void dfx_tc_stats_sync(dfx_index* idx) {
+    if (!idx->tc_stat_pending) return;
+    cudaEventSynchronize(idx->tc_stat_ev);
+    tc_stats_poll(idx);
+}
+static void tc_stats_post(dfx_index* idx, const int32_t* ovf, int64_t rows, bool fast, cudaStream_t st) {
+    if (idx->tc_mode != 0 || idx->tc_stat_pending || tc_stream_capturing(st)) return;
+    if (!idx->tc_stat_h) {
+        DFX_CUDA(cudaMallocHost(reinterpret_cast<void**>(&idx->tc_stat_h), 8));
+        DFX_CUDA(cudaEventCreateWithFlags(&idx->tc_stat_ev, cudaEventDisableTiming));
+    }
+    DFX_CUDA(cudaMemcpyAsync(idx->tc_stat_h, ovf, 8, cudaMemcpyDeviceToHost, st));
+    DFX_CUDA(cudaEventRecord(idx->tc_stat_ev, st));
+    idx->tc_stat_pending = true;
+    idx->tc_stat_fast = fast;
+    idx->tc_stat_rows = rows;
+}
+static ScreenTol tc_tol(const dfx_index* idx, int d, bool fast) {
+    ScreenTol t;
+    t.rel = screen_tol_rel(d, fast);
+    t.rel_fast = (!fast && idx->tc_mode == 0) ? screen_tol_rel(d, true) : 0.f;
+    return t;
+}
+
+// screening pass: gmin[nq][ng] for a batch of rows against a table prepared by tc_prepare_table
+// (npl planes used; the table must hold at least npl); also leaves |q|^2 in idx->tc_qn
+static void tc_screen(dfx_index* idx, int d, const float* d_x, int64_t nq, const void* table_h, float table_scale,
+                      int npl, const float* cnorm, int64_t nlist, int metric, float* gmin, float* gmin2,
+                      uint8_t* gargc, cudaStream_t st) {
     using namespace tc;
     const int64_t nl_pad = dfx_ceil_div(nlist, TILE) * TILE;
     const int64_t nq_pad = dfx_ceil_div(nq, TILE) * TILE;
     const int ng = (int)(nl_pad / 32);
-    idx->tc_q.reserve((size_t)2 * nq_pad * d * 2);
-    DFX_LAUNCH(split_bf16_kernel, (unsigned)dfx_ceil_div(nq_pad * d, 256), 256, 0, st, d_x, nq, nq_pad, d,
-               idx->tc_q.as<__nv_bfloat16>());
+    idx->tc_q.reserve((size_t)npl * nq_pad * d * 2);
+    idx->tc_qmult.reserve((size_t)nq_pad * 4);
+    DFX_LAUNCH(f16_rows_kernel, (unsigned)dfx_ceil_div(nq_pad, 8), 256, 0, st, d_x, nq, nq_pad, d, 1, table_scale,
+               metric == DFX_METRIC_IP ? -1.f : -2.f, npl, idx->tc_q.as<__half>(), idx->tc_qmult.as<float>(),
+               (float*)nullptr);
 #ifdef DFX_EMU
-    emu_tc_screen(idx->tc_q.as<float>(), nq, static_cast<const float*>(cent_planes), nlist, nl_pad, d, cnorm, metric,
-                  gmin, gmin2, gargc, ng);
+    emu_tc_screen(idx->tc_q.as<__half>(), idx->tc_qmult.as<float>(), nq, nq_pad, static_cast<const __half*>(table_h),
+                  nlist, nl_pad, d, npl, cnorm, metric, gmin, gmin2, gargc, ng);
     return;
 #else
     CUtensorMap tmQ, tmC;
-    make_tmap(&tmQ, idx->tc_q.p, 2 * nq_pad, d);
-    make_tmap(&tmC, cent_planes, 2 * nl_pad, d);
+    make_tmap(&tmQ, idx->tc_q.p, npl * nq_pad, d);
+    make_tmap(&tmC, table_h, npl * nl_pad, d);
     const int qtiles = (int)(nq_pad / TILE), ctiles = (int)(nl_pad / TILE);
-    // enough CTAs to fill the machine a few times over, each walking a contiguous range of
-    // centroid tiles with its query tile resident
-    // split the centroid tiles so that the grid is close to a whole number of 148-CTA waves
-    // (one CTA per SM) while every CTA keeps enough tiles to amortise loading its query tile:
+    const int katoms = d / KATOM;
+    // resident only for the k-atom counts the kernel is instantiated for (1, 2, 4); others stream
+    const bool res = Smem::resident(katoms, npl) && (katoms == 1 || katoms == 2 || katoms == 4);
+    const size_t smem = (size_t)Smem::total(res, katoms, npl) + 1024;
+    const int slots = 148 * ((npl == 1 && smem <= 113 * 1024) ? 2 : 1);  // CTAs resident at once
+    // split the centroid tiles so that the grid is close to a whole number of waves while every
+    // CTA keeps enough tiles to amortise its start (TMEM allocation, query tile, pipeline fill):
     // cost model = waves x (tiles per CTA + ~3 tiles of fixed overhead)
     int csplit = 1, per = ctiles;
     {
@@ -835,7 +1099,7 @@ static void tc_screen(dfx_index* idx, int d, const float* d_x, int64_t nq, const
             const int cs_eff = (int)dfx_ceil_div(ctiles, pr);
             if (cs_eff != cs) continue;
             const int64_t ctas = (int64_t)qtiles * cs;
-            const double waves = (double)dfx_ceil_div(ctas, 148);
+            const double waves = (double)dfx_ceil_div(ctas, slots);
             const double cost = waves * (pr + 3.0);
             if (cost < best_cost - 1e-9) {
                 best_cost = cost;
@@ -844,29 +1108,48 @@ static void tc_screen(dfx_index* idx, int d, const float* d_x, int64_t nq, const
             }
         }
     }
-    const int katoms = d / KATOM;
-    const size_t smem = (size_t)Smem::total(katoms) + 1024;
     dim3 grid((unsigned)csplit, (unsigned)qtiles);
     DFX_REQUIRE(qtiles <= 65535, "too many query tiles in one screening launch");
-#define DFX_TC_LAUNCH(KA, MT)                                                                            \
+#define DFX_TC_LAUNCH(KT_, MT, NP)                                                                       \
     do {                                                                                                 \
-        auto kern = tc_coarse_kernel<KA, MT>;                                                            \
+        auto kern = tc_coarse_kernel<KT_, MT, NP>;                                                       \
         DFX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
-        DFX_LAUNCH(kern, grid, THREADS, smem, st, tmQ, tmC, (int)nq, (int)nq_pad, (int)nlist, (int)nl_pad, \
-                   cnorm, metric, per, gmin, gmin2, gargc, ng);                                          \
+        DFX_LAUNCH(kern, grid, THREADS, smem, st, tmQ, tmC, (int)nq, (int)nq_pad, (int)nlist, (int)nl_pad, katoms, \
+                   cnorm, idx->tc_qmult.as<float>(), per, gmin, gmin2, gargc, ng);                       \
     } while (0)
-    if (katoms == 2 && metric == DFX_METRIC_L2) DFX_TC_LAUNCH(2, DFX_METRIC_L2);
-    else if (katoms == 2) DFX_TC_LAUNCH(2, DFX_METRIC_IP);
-    else if (metric == DFX_METRIC_L2) DFX_TC_LAUNCH(1, DFX_METRIC_L2);
-    else DFX_TC_LAUNCH(1, DFX_METRIC_IP);
+#define DFX_TC_LAUNCH_M(KT_, NP)                                          \
+    do {                                                                  \
+        if (metric == DFX_METRIC_L2) DFX_TC_LAUNCH(KT_, DFX_METRIC_L2, NP); \
+        else DFX_TC_LAUNCH(KT_, DFX_METRIC_IP, NP);                       \
+    } while (0)
+    // resident shapes get their k-atom count at compile time (npl * katoms <= 4)
+    if (npl == 1) {
+        if (res && katoms == 1) DFX_TC_LAUNCH_M(1, 1);
+        else if (res && katoms == 2) DFX_TC_LAUNCH_M(2, 1);
+        else if (res && katoms == 4) DFX_TC_LAUNCH_M(4, 1);
+        else DFX_TC_LAUNCH_M(0, 1);
+    } else {
+        if (res && katoms == 1) DFX_TC_LAUNCH_M(1, 2);
+        else if (res && katoms == 2) DFX_TC_LAUNCH_M(2, 2);
+        else DFX_TC_LAUNCH_M(0, 2);
+    }
+#undef DFX_TC_LAUNCH_M
 #undef DFX_TC_LAUNCH
 #endif  // DFX_EMU
+}
+
+// the overflow record of a decide launch: [overflow rows, FAST-would-overflow rows, row list ...]
+static int32_t* tc_ovf_reset(dfx_index* idx, int64_t nrows, cudaStream_t st) {
+    idx->tc_ovf.reserve((size_t)(nrows + 2) * 4);
+    DFX_CUDA(cudaMemsetAsync(idx->tc_ovf.p, 0, 8, st));
+    return idx->tc_ovf.as<int32_t>();
 }
 
 // top-nprobe lists per query -> keys int32 [nq, nprobe] (exactly the oracle's coarse result)
 void dfx_tc_coarse_search(dfx_index* idx, const float* d_x, int64_t nq, int nprobe, int32_t* keys, cudaStream_t st) {
     const int d = idx->cfg.d;
     const int64_t nlist = idx->cfg.nlist;
+    const int metric = idx->cfg.metric;
     const int64_t nl_pad = dfx_ceil_div(nlist, tc::TILE) * tc::TILE;
     const int ng = (int)(nl_pad / 32);
     int G = nprobe + 8;
@@ -877,44 +1160,50 @@ void dfx_tc_coarse_search(dfx_index* idx, const float* d_x, int64_t nq, int npro
     idx->tc_gmin2.reserve((size_t)qmax * ng * 4);
     idx->tc_gargc.reserve((size_t)qmax * ng);
     idx->tc_groups.reserve((size_t)qmax * G * 4);
+    const float* cent = idx->centroids.as<float>();
+    const float* cnorm = idx->cnorm.as<float>();
+    float* gmin = idx->tc_gmin.as<float>();
+    float* gmin2 = idx->tc_gmin2.as<float>();
+    uint8_t* gargc = idx->tc_gargc.as<uint8_t>();
+    int32_t* groups = idx->tc_groups.as<int32_t>();
+    tc_stats_poll(idx);
+    const bool fast = idx->tc_fast;
+    const ScreenTol tol = tc_tol(idx, d, fast);
     for (int64_t q0 = 0; q0 < nq; q0 += QC) {
         const int64_t qc = std::min(QC, nq - q0);
-        tc_screen(idx, d, d_x + q0 * d, qc, idx->tc_cent.p, idx->cnorm.as<float>(), nlist, idx->cfg.metric,
-                  idx->tc_gmin.as<float>(), idx->tc_gmin2.as<float>(), idx->tc_gargc.as<uint8_t>(), st);
+        const float* xq = d_x + q0 * d;
+        int32_t* kq = keys + q0 * nprobe;
+        tc_screen(idx, d, xq, qc, idx->tc_cent.p, idx->tc_cscale, fast ? 1 : 2, cnorm, nlist, metric, gmin, gmin2,
+                  gargc, st);
         if (G <= 32 && ng >= 32) {
             auto tk = topg_collect_kernel<256>;
-            DFX_LAUNCH(tk, (unsigned)dfx_ceil_div(qc, 8), 256, 0, st, idx->tc_gmin.as<float>(), qc, ng, G,
-                       idx->tc_groups.as<int32_t>());
+            DFX_LAUNCH(tk, (unsigned)dfx_ceil_div(qc, 8), 256, 0, st, gmin, qc, ng, G, groups);
         } else {
-            dfx_launch_select_cols(idx->tc_gmin.as<float>(), qc, ng, ng, G, 0, idx->tc_groups.as<int32_t>(),
-                                   nullptr, nullptr, 0, st);
+            dfx_launch_select_cols(gmin, qc, ng, ng, G, 0, groups, nullptr, nullptr, 0, st);
         }
+        int32_t* ovf = tc_ovf_reset(idx, qc, st);
         const int P_cand = dfx_next_pow2(G * 32 < 32 ? 32 : G * 32);
         if (nprobe <= 32 && G <= 64 && d % 4 == 0) {  // warp per query
             const size_t smem = (size_t)RR2_WARPS * ((d + 3) / 4 * 4) * 4 + (size_t)RR2_WARPS * G * 32 * 4;
-            DFX_LAUNCH(rerank2_kernel, (unsigned)dfx_ceil_div(qc, RR2_WARPS), RR2_WARPS * 32, smem, st, d_x + q0 * d, d,
-                       idx->centroids.as<float>(), idx->cnorm.as<float>(), nlist, idx->cfg.metric,
-                       idx->tc_groups.as<int32_t>(), G, nprobe, idx->tc_gmin.as<float>(), idx->tc_gmin2.as<float>(),
-                       idx->tc_gargc.as<uint8_t>(), ng, idx->tc_cmax2, qc, keys + q0 * nprobe);
+            DFX_LAUNCH(rerank2_kernel, (unsigned)dfx_ceil_div(qc, RR2_WARPS), RR2_WARPS * 32, smem, st, xq, d, cent,
+                       cnorm, nlist, metric, groups, G, nprobe, gmin, gmin2, gargc, ng, idx->tc_cmax2, tol, qc, kq, ovf);
         } else if (P_cand <= 4096) {  // fused: candidates never leave the SM
             auto kern = rerank_kernel<2>;
             const size_t smem = ((size_t)d * 4 + 15) / 16 * 16 + (size_t)P_cand * 8;
-            DFX_LAUNCH(kern, (unsigned)qc, 128, smem, st, d_x + q0 * d, d, idx->centroids.as<float>(),
-                       idx->cnorm.as<float>(), nlist, idx->cfg.metric, idx->tc_groups.as<int32_t>(), G, nprobe,
-                       idx->tc_gmin.as<float>(), idx->tc_gmin2.as<float>(), idx->tc_gargc.as<uint8_t>(), ng,
-                       idx->tc_cmax2, (uint64_t*)nullptr, (int32_t*)nullptr, (const int32_t*)nullptr,
-                       (const int32_t*)nullptr, qc, keys + q0 * nprobe);
+            DFX_LAUNCH(kern, (unsigned)qc, 128, smem, st, xq, d, cent, cnorm, nlist, metric, groups, G, nprobe, gmin,
+                       gmin2, gargc, ng, idx->tc_cmax2, tol, (uint64_t*)nullptr, (int32_t*)nullptr,
+                       (const int32_t*)nullptr, (const int32_t*)nullptr, qc, kq, ovf);
         } else {
             idx->tc_cand.reserve((size_t)qmax * G * 32 * 8);
             auto kern = rerank_kernel<0>;
-            DFX_LAUNCH(kern, (unsigned)qc, 128, (size_t)d * 4, st, d_x + q0 * d, d, idx->centroids.as<float>(),
-                       idx->cnorm.as<float>(), nlist, idx->cfg.metric, idx->tc_groups.as<int32_t>(), G, nprobe,
-                       idx->tc_gmin.as<float>(), idx->tc_gmin2.as<float>(), idx->tc_gargc.as<uint8_t>(), ng,
-                       idx->tc_cmax2, idx->tc_cand.as<uint64_t>(), (int32_t*)nullptr, (const int32_t*)nullptr,
-                       (const int32_t*)nullptr, qc, (int32_t*)nullptr);
-            dfx_launch_select_comp(idx->tc_cand.as<uint64_t>(), qc, G * 32, (int64_t)G * 32, nprobe,
-                                   keys + q0 * nprobe, st);
+            DFX_LAUNCH(kern, (unsigned)qc, 128, (size_t)d * 4, st, xq, d, cent, cnorm, nlist, metric, groups, G,
+                       nprobe, gmin, gmin2, gargc, ng, idx->tc_cmax2, tol, idx->tc_cand.as<uint64_t>(),
+                       (int32_t*)nullptr, (const int32_t*)nullptr, (const int32_t*)nullptr, qc, (int32_t*)nullptr, ovf);
+            dfx_launch_select_comp(idx->tc_cand.as<uint64_t>(), qc, G * 32, (int64_t)G * 32, nprobe, kq, st);
         }
+        // rows with more near-ties than selected groups (screen_overflow): exact, over all lists
+        launch_exact_rows(xq, cent, cnorm, nlist, d, metric, ovf, qc, 2, nprobe, kq, nullptr, nullptr, st);
+        if (q0 + QC >= nq) tc_stats_post(idx, ovf, qc, fast, st);
     }
 }
 
@@ -935,10 +1224,7 @@ int dfx_tc_flat_candidates(dfx_index* idx, const float* d_x, int64_t nq, int k, 
     const int metric = idx->cfg.metric;
     const int64_t nl_pad = dfx_ceil_div(N, tc::TILE) * tc::TILE;
     const int ng = (int)(nl_pad / 32);
-    if (idx->tc_flat_rows != N) {  // (re)build the planes and the norm bound
-        idx->tc_cent.reserve((size_t)2 * nl_pad * d * 2);
-        DFX_LAUNCH(split_bf16_kernel, (unsigned)dfx_ceil_div(nl_pad * d, 256), 256, 0, st, idx->payload.as<float>(), N,
-                   nl_pad, d, idx->tc_cent.as<__nv_bfloat16>());
+    if (idx->tc_flat_rows != N) {  // (re)build the fp16 copy of the rows and the norm bound
         const float* norms = idx->xnorm.as<float>();
         if (metric != DFX_METRIC_L2) {  // inner product keeps no row norms: the tolerance needs their maximum
             idx->cnorm.reserve((size_t)N * 4);
@@ -946,8 +1232,15 @@ int dfx_tc_flat_candidates(dfx_index* idx, const float* d_x, int64_t nq, int k, 
             norms = idx->cnorm.as<float>();
         }
         idx->tc_cmax2 = max_norm2(idx, norms, N, st);
+        idx->tc_cscale = tc_prepare_table(idx->payload.as<float>(), N, d, idx->tc_cmax2, 2, idx->tc_cent, st);
+        idx->tc_cent_npl = 2;
         idx->tc_flat_rows = N;
+        if (idx->tc_mode == 0) idx->tc_fast = false;  // AUTO: new rows start PRECISE
+        idx->tc_stat_pending = false;
     }
+    tc_stats_poll(idx);
+    const bool fast = idx->tc_fast;
+    const ScreenTol tol = tc_tol(idx, d, fast);
     int G = k + 8;
     if (G > ng) G = ng;
     const int ncand = G * 32;
@@ -956,8 +1249,8 @@ int dfx_tc_flat_candidates(dfx_index* idx, const float* d_x, int64_t nq, int k, 
     idx->tc_gargc.reserve((size_t)nq * ng);
     idx->tc_groups.reserve((size_t)nq * G * 4);
     idx->tc_cand.reserve((size_t)nq * ncand * 8);
-    tc_screen(idx, d, d_x, nq, idx->tc_cent.p, idx->xnorm.as<float>(), N, metric, idx->tc_gmin.as<float>(),
-              idx->tc_gmin2.as<float>(), idx->tc_gargc.as<uint8_t>(), st);
+    tc_screen(idx, d, d_x, nq, idx->tc_cent.p, idx->tc_cscale, fast ? 1 : 2, idx->xnorm.as<float>(), N, metric,
+              idx->tc_gmin.as<float>(), idx->tc_gmin2.as<float>(), idx->tc_gargc.as<uint8_t>(), st);
     if (G <= 32 && ng >= 32) {
         auto tk = topg_collect_kernel<256>;
         DFX_LAUNCH(tk, (unsigned)dfx_ceil_div(nq, 8), 256, 0, st, idx->tc_gmin.as<float>(), nq, ng, G,
@@ -966,11 +1259,16 @@ int dfx_tc_flat_candidates(dfx_index* idx, const float* d_x, int64_t nq, int k, 
         dfx_launch_select_cols(idx->tc_gmin.as<float>(), nq, ng, ng, G, 0, idx->tc_groups.as<int32_t>(), nullptr,
                                nullptr, 0, st);
     }
+    int32_t* ovf = tc_ovf_reset(idx, nq, st);
     auto kern = rerank_kernel<0>;
     DFX_LAUNCH(kern, (unsigned)nq, 128, (size_t)d * 4, st, d_x, d, idx->payload.as<float>(), idx->xnorm.as<float>(), N,
                metric, idx->tc_groups.as<int32_t>(), G, k, idx->tc_gmin.as<float>(), idx->tc_gmin2.as<float>(),
-               idx->tc_gargc.as<uint8_t>(), ng, idx->tc_cmax2, idx->tc_cand.as<uint64_t>(), (int32_t*)nullptr,
-               (const int32_t*)nullptr, (const int32_t*)nullptr, nq, (int32_t*)nullptr);
+               idx->tc_gargc.as<uint8_t>(), ng, idx->tc_cmax2, tol, idx->tc_cand.as<uint64_t>(), (int32_t*)nullptr,
+               (const int32_t*)nullptr, (const int32_t*)nullptr, nq, (int32_t*)nullptr, ovf);
+    // rows with more near-ties than selected groups: their ncand slots become the exact top-ncand
+    launch_exact_rows(d_x, idx->payload.as<float>(), idx->xnorm.as<float>(), N, d, metric, ovf, nq, 0, ncand, nullptr,
+                      nullptr, idx->tc_cand.as<uint64_t>(), st);
+    tc_stats_post(idx, ovf, nq, fast, st);
     return ncand;
 }
 
@@ -980,7 +1278,9 @@ void dfx_tc_assign(dfx_index* idx, int d, const float* d_cent, const float* d_cn
                    int64_t n, const float* d_x, int32_t* d_assign, cudaStream_t st) {
     const int64_t nl_pad = dfx_ceil_div(nlist, tc::TILE) * tc::TILE;
     const int ng = (int)(nl_pad / 32);
-    constexpr int G = 2;
+    // groups kept per row: the best one decides, the others tell whether it does so unambiguously;
+    // a row whose G-th group is still within the tolerance goes to the exact fallback
+    const int G = ng < 6 ? ng : 6;
     const int64_t RC = std::max<int64_t>(tc::TILE, ((256ll << 20) / ((int64_t)ng * 4)) / tc::TILE * tc::TILE);
     const int64_t rmax = std::min<int64_t>(n, RC);
     idx->tc_gmin.reserve((size_t)rmax * ng * 4);
@@ -989,32 +1289,53 @@ void dfx_tc_assign(dfx_index* idx, int d, const float* d_cent, const float* d_cn
     idx->tc_groups.reserve((size_t)rmax * G * 4);
     idx->tc_qn.reserve((size_t)rmax * 4);
     idx->tc_amb.reserve((size_t)(rmax + 1) * 4);
-    // bf16 planes of this centroid table (k-means changes it every iteration; splitting is cheap)
-    idx->tc_cent_tmp.reserve((size_t)2 * nl_pad * d * 2);
-    DFX_LAUNCH(split_bf16_kernel, (unsigned)dfx_ceil_div(nl_pad * d, 256), 256, 0, st, d_cent, nlist, nl_pad, d,
-               idx->tc_cent_tmp.as<__nv_bfloat16>());
-    const void* cent_planes = idx->tc_cent_tmp.p;
+    // fp16 copy of this centroid table (k-means changes it every iteration; converting is cheap).
+    // Precision: tc_mode 1 / 2 as set; AUTO decides per chunk from the counts of the chunk before
+    // (read back with a sync -- this is the build path), starting PRECISE on every call.
     const float cmax2 = max_norm2(idx, d_cnorm, nlist, st);
-    for (int64_t r0 = 0; r0 < n; r0 += RC) {
-        const int64_t rc = std::min(RC, n - r0);
+    const float cscale = tc_prepare_table(d_cent, nlist, d, cmax2, 2, idx->tc_cent_tmp, st);
+    bool fast = idx->tc_mode == 1;
+    for (int64_t r0 = 0, rc = 0; r0 < n; r0 += rc) {
+        // the first AUTO chunk is a small PRECISE probe, so that most of the rows run at the
+        // precision their statistics call for
+        rc = (idx->tc_mode == 0 && r0 == 0) ? std::min<int64_t>(n, 64 * tc::TILE) : std::min(RC, n - r0);
         const float* xr = d_x + r0 * d;
-        tc_screen(idx, d, xr, rc, cent_planes, d_cnorm, nlist, metric, idx->tc_gmin.as<float>(),
-                  idx->tc_gmin2.as<float>(), idx->tc_gargc.as<uint8_t>(), st);
-        auto topg = topg_small_kernel<G>;
-        DFX_LAUNCH(topg, (unsigned)dfx_ceil_div(rc, 8), 256, 0, st, idx->tc_gmin.as<float>(), rc, ng,
-                   idx->tc_groups.as<int32_t>());
+        ScreenTol tol;
+        tol.rel = screen_tol_rel(d, fast);
+        tol.rel_fast = 0.f;  // counted once per row by assign_resolve_kernel
+        const float rel_fast = (!fast && idx->tc_mode == 0) ? screen_tol_rel(d, true) : 0.f;
+        tc_screen(idx, d, xr, rc, idx->tc_cent_tmp.p, cscale, fast ? 1 : 2, d_cnorm, nlist, metric,
+                  idx->tc_gmin.as<float>(), idx->tc_gmin2.as<float>(), idx->tc_gargc.as<uint8_t>(), st);
+        if (ng >= 32) {
+            auto tk = topg_collect_kernel<256>;
+            DFX_LAUNCH(tk, (unsigned)dfx_ceil_div(rc, 8), 256, 0, st, idx->tc_gmin.as<float>(), rc, ng, G,
+                       idx->tc_groups.as<int32_t>());
+        } else {
+            dfx_launch_select_cols(idx->tc_gmin.as<float>(), rc, ng, ng, G, 0, idx->tc_groups.as<int32_t>(), nullptr,
+                                   nullptr, 0, st);
+        }
         dfx_launch_row_norms(xr, rc, d, idx->tc_qn.as<float>(), st);
         int32_t* amb_count = idx->tc_amb.as<int32_t>();
         int32_t* amb_rows = amb_count + 1;
         DFX_CUDA(cudaMemsetAsync(amb_count, 0, 4, st));
+        int32_t* ovf = tc_ovf_reset(idx, rc, st);
         DFX_LAUNCH(assign_resolve_kernel, (unsigned)dfx_ceil_div(rc, 256), 256, 0, st, idx->tc_qn.as<float>(),
                    idx->tc_groups.as<int32_t>(), idx->tc_gmin.as<float>(), idx->tc_gmin2.as<float>(),
-                   idx->tc_gargc.as<uint8_t>(), ng, cmax2, rc, d_assign + r0, amb_rows, amb_count);
+                   idx->tc_gargc.as<uint8_t>(), ng, G, cmax2, tol.rel, rel_fast, rc, d_assign + r0, amb_rows,
+                   amb_count, ovf);
         auto kern = rerank_kernel<1>;
         const unsigned grid = (unsigned)std::min<int64_t>(rc, 148 * 16);
         DFX_LAUNCH(kern, grid, 128, (size_t)d * 4, st, xr, d, d_cent, d_cnorm, nlist, metric,
                    idx->tc_groups.as<int32_t>(), G, 1, idx->tc_gmin.as<float>(), idx->tc_gmin2.as<float>(),
-                   idx->tc_gargc.as<uint8_t>(), ng, cmax2, (uint64_t*)nullptr, d_assign + r0,
-                   (const int32_t*)amb_rows, (const int32_t*)amb_count, rc, (int32_t*)nullptr);
+                   idx->tc_gargc.as<uint8_t>(), ng, cmax2, tol, (uint64_t*)nullptr, d_assign + r0,
+                   (const int32_t*)amb_rows, (const int32_t*)amb_count, rc, (int32_t*)nullptr, ovf);
+        launch_exact_rows(xr, d_cent, d_cnorm, nlist, d, metric, ovf, rc, 1, 1, nullptr, d_assign + r0, nullptr, st);
+        if (idx->tc_mode == 0 && r0 + rc < n) {  // AUTO: the next chunk's precision
+            int32_t h[2] = {0, 0};
+            DFX_CUDA(cudaMemcpyAsync(h, ovf, 8, cudaMemcpyDeviceToHost, st));
+            DFX_CUDA(cudaStreamSynchronize(st));
+            if (fast && (int64_t)h[0] * 64 > rc) fast = false;
+            else if (!fast && (int64_t)h[1] * 256 <= rc) fast = true;
+        }
     }
 }

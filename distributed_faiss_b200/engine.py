@@ -29,7 +29,7 @@ KIND_NAMES = {KIND_FLAT: "flat", KIND_IVF_FLAT: "ivf_flat", KIND_IVF_PQ: "ivf_pq
 
 # every symbol include/dfx.h declares (tests check that the library exports each one)
 EXPORTED_SYMBOLS = [
-    "dfx_create", "dfx_destroy", "dfx_train", "dfx_add", "dfx_train_dev", "dfx_add_dev", "dfx_set_param",
+    "dfx_create", "dfx_destroy", "dfx_train", "dfx_add", "dfx_train_dev", "dfx_add_dev", "dfx_set_param", "dfx_get_param",
     "dfx_reserve", "dfx_finalize", "dfx_search", "dfx_search_dev", "dfx_reconstruct", "dfx_set_nprobe",
     "dfx_get_nprobe", "dfx_generation", "dfx_ntotal", "dfx_nlist", "dfx_is_trained", "dfx_get_centroids", "dfx_merge",
     "dfx_merge_dev", "dfx_merge_packed_dev", "dfx_encode_ids_dev", "dfx_filter_compact_dev",
@@ -158,6 +158,11 @@ class GpuIndex:
 
     def set_param(self, name, value):
         _check(lib().dfx_set_param(self._h, name.encode(), C.c_double(float(value))))
+
+    def get_param(self, name):
+        v = C.c_double(0.0)
+        _check(lib().dfx_get_param(self._h, name.encode(), C.byref(v)))
+        return v.value
 
     def reserve(self, n_total):
         _check(lib().dfx_reserve(self._h, C.c_int64(int(n_total))))

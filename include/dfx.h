@@ -67,24 +67,28 @@ int dfx_train(dfx_index *idx, int64_t n, const float *x);
 int dfx_add(dfx_index *idx, int64_t n, const float *x);
 int dfx_train_dev(dfx_index *idx, int64_t n, const float *d_x, void *stream);
 int dfx_add_dev(dfx_index *idx, int64_t n, const float *d_x, void *stream);
-/* training knobs: "kmeans_niter" (default 25), "max_points_per_centroid" (256),
- * "train_seed" (1234) -- the faiss Clustering defaults; "tensor_cores" (1): 0 forces the plain
- * fp32 FFMA coarse quantizer instead of the tcgen05 screening path (same results);
- * "interleaved" (1): 0 keeps IVF-PQ codes row-major and scans them one vector per lane
- * instead of the interleaved lane-per-subquantizer layout (same results);
- * "scan_variant" (1): 2 selects the experimental lane-per-vector block layout and scan kernel
- * (dfx_scan_il2.cu; same results by construction, not yet validated on hardware), 3 the default
- * kernel on a block layout whose 128-bit loads are contiguous (same status);
- * "prep_variant" (1): 2 selects the experimental table-building kernel pq_prep2_kernel (same);
- * "scan_ring" (0): 1 feeds scan variant 2 through per-warp cp.async.bulk rings in shared memory
- * (experimental, same results);
- * "rows_inflight" (4): 8 keeps eight instead of four vectors per warp in flight in the
- * IVF-Flat / IVF-SQ list scan (experimental, same results);
- * "flat_tensor_cores" (0): 1 runs FLAT searches through the tensor-core screening + exact re-rank
- * instead of the FFMA GEMM (experimental, same results);
- * "rerank_variant" (1): 2 selects the experimental warp-per-query exact re-rank of the coarse
- * quantizer's tensor-core path (same) */
+/* knobs (every setting returns the same results; they only move the cost):
+ * training: "kmeans_niter" (default 25), "max_points_per_centroid" (256), "train_seed" (1234) --
+ *   the faiss Clustering defaults;
+ * "tensor_cores" (1): 0 forces the plain fp32 FFMA coarse quantizer instead of the tcgen05
+ *   screening path;
+ * "tc_screen_mode" (0): precision of the tcgen05 screening: 0 = AUTO (starts PRECISE, moves to
+ *   FAST once a launch shows FAST's wider tolerance would not overflow the kept groups, and back),
+ *   1 = FAST (fp16 operands, one MMA per k-step), 2 = PRECISE (fp16 hi/lo split, three MMAs);
+ * "flat_tensor_cores" (1): 0 runs FLAT searches through the FFMA GEMM instead of the tensor-core
+ *   screening + exact re-rank;
+ * "interleaved" (1): 0 keeps IVF-PQ (M = 32) codes row-major (one vector per lane, table from
+ *   pq_prep_kernel) instead of the block-interleaved layout of the fused table-build + scan;
+ * "il2_threads" (0 = 256) / "il2_prefetch" (-1 = 4 blocks): CTA shape and L2 prefetch distance of
+ *   that scan (tuning);
+ * "rows_inflight" (0 = by row size): 4 or 8 vectors per warp in flight in the IVF-Flat / IVF-SQ
+ *   list scan */
 int dfx_set_param(dfx_index *idx, const char *name, double value);
+/* read back a knob or a counter: the names of dfx_set_param, plus "tc_fast" (the precision the
+ * next screening launch will use: 1 = FAST), "tc_stat_rows" / "tc_stat_overflow" /
+ * "tc_stat_fast_would" (rows, rows re-done exactly, and rows FAST would have re-done, of the last
+ * launch whose statistics came back; synchronises with that launch) */
+int dfx_get_param(dfx_index *idx, const char *name, double *value);
 /* pre-size the shard for n_total vectors (optional; avoids regrowth while bulk loading) */
 int dfx_reserve(dfx_index *idx, int64_t n_total);
 /* fold pending adds into the inverted lists now (otherwise done by the next search) */

@@ -28,6 +28,10 @@ METRICS = [
     "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
     "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio",
     "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
+    "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active",
+    "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "l1tex__data_pipe_tc_wavefronts_mem_shared.sum",
+    "l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed", "smsp__mem_tensor_reads_op_ldt.sum",
 ]
 
 
@@ -40,12 +44,16 @@ def main():
     for r in rows[2:]:
         d = {"kernel": r[hdr.index("Kernel Name")].split("(")[0]}
         for m in hdr:
-            if m in METRICS or "tensor" in m and ("pct" in m or m.endswith(".sum")):
+            tensor = "tensor" in m and (m.endswith(".avg.pct_of_peak_sustained_elapsed") or m.endswith(".sum"))
+            if m in METRICS or tensor:
                 i = hdr.index(m)
                 try:
-                    d[m] = float(r[i].replace(",", ""))
+                    v = float(r[i].replace(",", ""))
                 except ValueError:
-                    d[m] = r[i]
+                    v = r[i]
+                if tensor and m not in METRICS and v == 0.0:
+                    continue   # the tensor-pipe breakdown: only the paths a kernel actually uses
+                d[m] = v
                 d[m + "__unit"] = units[i]
         res.append(d)
     json.dump({"report": rep, "kernels": res}, open(out, "w"), indent=1)

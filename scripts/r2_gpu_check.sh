@@ -19,6 +19,10 @@ echo "== ncu launch list of the timed region"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off -c 400 --csv \
     --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 2 --warmup 1 --no-cpu --no-sweep > gpurun_out/${TAG}_ncu_list.log 2>&1
 tail -2 gpurun_out/${TAG}_ncu_list.log
+echo "== ncu full capture of the coarse-quantizer screening kernel (search shape)"
+timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:tc_coarse -c 2 \
+    -o gpurun_out/${TAG}_tc_coarse python bench.py --steps 1 --warmup 1 --no-cpu --no-sweep > gpurun_out/${TAG}_ncu_full_tc.log 2>&1
+tail -2 gpurun_out/${TAG}_ncu_full_tc.log
 echo "== ncu full capture of the scan kernel"
 timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:scan_pq_il2 -c 2 \
     -o gpurun_out/${TAG}_scan_pq_il2 python bench.py --steps 1 --warmup 1 --no-cpu --no-sweep > gpurun_out/${TAG}_ncu_full.log 2>&1

@@ -1,7 +1,8 @@
+#!/bin/bash
+# One 125 M-vector shard of the bench workload: scan-kernel variants in round robin
+# (MB_VARIANTS="threads:prefetch,..."), the gap statistics the screening tolerance is up against,
+# and the coarse-quantizer precision modes.   gpurun --timeout 900 -- 'bash scripts/r2_microbench.sh'
 set -u
 mkdir -p gpurun_out
-echo "== gpu suite"
-timeout 1500 python -m pytest tests -m gpu -q -x 2>&1 | tail -15 | tee gpurun_out/r2c_suite.log
-for pf in 0 2 4 8 16; do
-  DFX_IL2_PREFETCH=$pf timeout 300 python scripts/scan_microbench.py pf$pf 2>/dev/null | tail -1 | tee -a gpurun_out/r2c_microbench.jsonl
-done
+MB_VARIANTS="${MB_VARIANTS:-256:2,256:4,256:8,512:2}" MB_REPS="${MB_REPS:-3}" timeout 600 python scripts/scan_microbench.py mb \
+    2>gpurun_out/mb.err | tail -1 | tee gpurun_out/microbench.json

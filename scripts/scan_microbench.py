@@ -37,32 +37,86 @@ def main():
     # MB_VARIANTS="threads:prefetch,..." e.g. "256:4,256:0,512:4" (dfx_set_param il2_threads / il2_prefetch)
     variants = [tuple(int(x) for x in v.split(":")) for v in os.environ.get("MB_VARIANTS", "0:-1").split(",")]
     ref = None
-    for (thr, pf) in variants:
-      idx.set_param("il2_threads", thr)
-      idx.set_param("il2_prefetch", pf)
-      for B in (4096,):
-          batches = [xq[i * B:(i + 1) * B].contiguous() for i in range(12288 // B)]
-          for b in batches:
-              idx.search_dev(b, 10)
-          torch.cuda.synchronize()
-          ndis = idx.last_stats()["ndis"]
-          idx.profile(True)
-          idx.profile_read(True)
-          e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-          e0.record()
-          n = 30
-          for i in range(n):
-              idx.search_dev(batches[i % len(batches)], 10)
-          e1.record()
-          torch.cuda.synchronize()
-          ms, nl = idx.profile_read(True)
-          idx.profile(False)
-          Dv, Iv = idx.search_dev(batches[0], 10)
-          if ref is None:
-              ref = (Dv.clone(), Iv.clone())
-          same = bool(torch.equal(Dv, ref[0]) and torch.equal(Iv, ref[1]))
-          out[f"t{thr}_pf{pf}_B{B}"] = {"same_as_first_variant": same, "scan_ms_per_launch": ms / nl, "search_ms": e0.elapsed_time(e1) / n,
-                          "algorithmic_GBps": ndis * 32 / (ms / nl) / 1e6, "frac_of_6568": ndis * 32 / (ms / nl) / 1e6 / 6568.4}
+    B = 4096
+    batches = [xq[i * B:(i + 1) * B].contiguous() for i in range(12288 // B)]
+    reps = int(os.environ.get("MB_REPS", 3))
+    acc = {}
+    # round robin over the variants, `reps` times: clocks drift under sustained load, so a variant
+    # is only comparable with its neighbours in time; the median over the rounds is reported
+    for rep in range(reps):
+        for (thr, pf) in variants:
+            idx.set_param("il2_threads", thr)
+            idx.set_param("il2_prefetch", pf)
+            for b in batches:
+                Dv, Iv = idx.search_dev(b, 10)
+            torch.cuda.synchronize()
+            if ref is None:
+                ref = (Dv.clone(), Iv.clone())
+            same = bool(torch.equal(Dv, ref[0]) and torch.equal(Iv, ref[1]))
+            ndis = idx.last_stats()["ndis"]
+            idx.profile(True)
+            idx.profile_read(True)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            last = rep == reps - 1 and (thr, pf) == variants[-1]
+            if last:
+                torch.cuda.profiler.start()   # ncu --profile-from-start off: the launch list of one variant
+            e0.record()
+            n = 12
+            for i in range(n):
+                idx.search_dev(batches[i % len(batches)], 10)
+            e1.record()
+            torch.cuda.synchronize()
+            if last:
+                torch.cuda.profiler.stop()
+            ms, nl = idx.profile_read(True)
+            idx.profile(False)
+            a = acc.setdefault(f"t{thr}_pf{pf}", {"scan_ms": [], "search_ms": [], "same": True, "ndis": ndis})
+            a["scan_ms"].append(ms / nl)
+            a["search_ms"].append(e0.elapsed_time(e1) / n)
+            a["same"] = a["same"] and same
+    for k, a in acc.items():
+        sm = float(np.median(a["scan_ms"]))
+        out[k] = {"same_as_first_variant": a["same"], "scan_ms_per_launch": sm, "scan_ms_all": a["scan_ms"],
+                  "search_ms": float(np.median(a["search_ms"])), "algorithmic_GBps": a["ndis"] * 32 / sm / 1e6,
+                  "frac_of_6568": a["ndis"] * 32 / sm / 1e6 / 6568.4}
+    # the distribution the screening tolerance is up against: gaps between the 8th, 9th and 16th
+    # smallest ranking values |c|^2 - 2 q.c of a query sample (exact fp32, torch)
+    cent = torch.from_numpy(idx.get_array("centroids").reshape(-1, bench.D)).cuda()
+    cn = (cent * cent).sum(1)
+    qs = batches[0][:512]
+    V = cn[None, :] - 2.0 * qs @ cent.t()
+    Vs = torch.sort(V, dim=1).values[:, :32]
+    qn = (qs * qs).sum(1).sqrt()
+    def qtl(t):
+        return [float(torch.quantile(t, q)) for q in (0.01, 0.1, 0.5, 0.9)]
+    out["gap_stats"] = {"cmax2": float(cn.max()), "cmean2": float(cn.mean()), "qnorm_mean": float(qn.mean()),
+                        "tc_cmax2": idx.get_param("tc_cmax2"),
+                        "gap_8_to_9": qtl(Vs[:, 8] - Vs[:, 7]), "gap_8_to_16": qtl(Vs[:, 15] - Vs[:, 7]),
+                        "gap_8_to_24": qtl(Vs[:, 23] - Vs[:, 7]), "v8": qtl(Vs[:, 7])}
+    del V, Vs
+    # coarse-quantizer screening precision: AUTO state after the runs above, then both fixed modes
+    stat_names = ("tc_fast", "tc_stat_rows", "tc_stat_overflow", "tc_stat_fast_would")
+    out["auto_state"] = {k: idx.get_param(k) for k in stat_names}
+    for mode, name in ((2, "precise"), (0, "auto")):
+        idx.set_param("tc_screen_mode", mode)
+        for b in batches:
+            idx.search_dev(b, 10)
+        torch.cuda.synchronize()
+        idx.profile(True)
+        idx.profile_read(True)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(12):
+            Dm, Im = idx.search_dev(batches[i % len(batches)], 10)
+        e1.record()
+        torch.cuda.synchronize()
+        ms, nl = idx.profile_read(True)
+        idx.profile(False)
+        Dm, Im = idx.search_dev(batches[-1], 10)
+        out["screen_" + name] = {"search_ms": e0.elapsed_time(e1) / 12, "scan_ms": ms / nl,
+                                 "coarse_ms": e0.elapsed_time(e1) / 12 - ms / nl,
+                                 "same": bool(torch.equal(Dm, ref[0]) and torch.equal(Im, ref[1])),
+                                 **{k: idx.get_param(k) for k in stat_names}}
     print(json.dumps(out))
 
 

@@ -41,6 +41,9 @@ SUBSET = [
     "tests/test_gpu_parity.py::test_tensor_core_coarse_quantizer_matches_oracle[ivf_flat-1-64-0]",
     "tests/test_gpu_parity.py::test_flat_tensor_core_path_matches_oracle[0]",    # flat_tensor_cores=1
     "tests/test_gpu_parity.py::test_flat_tensor_core_path_matches_oracle[1]",
+    # more near-ties than kept groups -> exact fallback; AUTO screening precision follows the data
+    "tests/test_gpu_parity.py::test_tensor_core_near_tie_overflow_is_redone_exactly",
+    "tests/test_gpu_parity.py::test_tensor_core_auto_precision_follows_the_data",
 ]
 
 

@@ -329,9 +329,10 @@ def test_device_pointer_path_matches_host_path():
 @pytest.mark.parametrize("kind,metric,d,M", [("ivf_pq", L2, 128, 32), ("ivf_flat", L2, 64, 0),
                                              ("ivf_flat", IP, 128, 0), ("ivf_sq", L2, 128, 0)])
 def test_tensor_core_coarse_quantizer_matches_oracle(kind, metric, d, M):
-    """nlist >= 1024 and d in {64,128} route the coarse quantizer through tcgen05 (bf16 split
-    screening) + canonical fp32 re-rank: probe lists, hence results, must still be bit-identical
-    to the oracle's, and identical to the plain FFMA path."""
+    """nlist >= 1024 and d a multiple of 64 route the coarse quantizer through tcgen05 (fp16
+    screening: FAST one MMA per k-step, PRECISE hi/lo split, AUTO choosing between them from the
+    statistics of the launch before) + canonical fp32 re-rank: probe lists, hence results, must
+    still be bit-identical to the oracle's in every mode, and identical to the plain FFMA path."""
     rs = np.random.RandomState(12)
     nlist, n = 1024, _sz(60_000, 6_000)
     g, o, xb = _build_both(kind, metric, d, nlist, M, n, rs, via="gpu")
@@ -340,9 +341,11 @@ def test_tensor_core_coarse_quantizer_matches_oracle(kind, metric, d, M):
         g.nprobe = nprobe; o.nprobe = nprobe
         Do, Io = o.search(xq, 10)
         g.set_param("tensor_cores", 1)
-        Dg, Ig = g.search(xq, 10)
-        _assert_same(Dg, Ig, Do, Io, f"TC coarse {kind} nprobe={nprobe}")
-        assert g.last_stats()["ndis"] == o.last_ndis
+        for mode, name in ((2, "precise"), (1, "fast"), (0, "auto"), (0, "auto, second launch")):
+            g.set_param("tc_screen_mode", mode)
+            Dg, Ig = g.search(xq, 10)
+            _assert_same(Dg, Ig, Do, Io, f"TC coarse ({name}) {kind} nprobe={nprobe}")
+            assert g.last_stats()["ndis"] == o.last_ndis
         g.set_param("tensor_cores", 0)
         Df, If = g.search(xq, 10)
         _assert_same(Df, If, Do, Io, f"FFMA coarse {kind} nprobe={nprobe}")
@@ -352,6 +355,89 @@ def test_tensor_core_coarse_quantizer_matches_oracle(kind, metric, d, M):
     D1, I1 = g.search(xq[3:4], 10)
     o.nprobe = 64
     _assert_same(D1, I1, *o.search(xq[3:4], 10), "TC coarse nq=1")
+
+
+def test_tensor_core_near_tie_overflow_is_redone_exactly():
+    """More near-tied group minima than the decide stage keeps (duplicate centroids, duplicate
+    database rows): the row is flagged (screen_overflow) and tc_exact_rows_kernel redoes it over
+    ALL columns, so probe lists / results stay bit-identical to the oracle's -- ids ascending
+    among exact ties, and the one populated list among 48 duplicate centroids is still probed."""
+    from oracle import oracle as O
+
+    E = _engine()
+    rs = np.random.RandomState(21)
+    d, nlist = 64, 2048
+    # (a) coarse quantizer (search) and assignment (add): 48 copies of one centroid, one per group of 32
+    cent = rs.randn(nlist, d).astype(np.float32)
+    # (at DEScending positions inside their groups: the packed column index orders equal screening
+    # values by position first, so without the exact fallback the LAST copies would be probed)
+    cols = 32 * np.arange(48) + (31 - np.arange(48) % 32)
+    cent[cols] = cent[cols[0]]
+    o = O.make_index("ivf_flat", d, metric=L2, nlist=nlist)
+    o.set_state({"centroids": cent, "list_off": np.zeros(nlist + 1, np.int64), "ids": np.zeros(0, np.int64),
+                 "vecs": np.zeros((0, d), np.float32)})
+    n = _sz(20_000, 3_000)
+    xb = (cent[rs.randint(0, nlist, n)] + 0.05 * rs.randn(n, d)).astype(np.float32)
+    xb[:200] = cent[cols[0]] + 0.01 * rs.randn(200, d).astype(np.float32)   # rows of the duplicated centroid
+    o.add(xb)
+    assert np.diff(o.list_off)[cols[1:]].sum() == 0   # ties -> smallest index: only the first copy's list is populated
+    g = E.GpuIndex(E.KIND_IVF_FLAT, d, L2, nlist=nlist)
+    g.set_state({"centroids": cent, "list_off": np.zeros(nlist + 1, np.int64), "ids": np.zeros(0, np.int64),
+                 "vecs": np.zeros((0, d), np.float32)})
+    g.add(xb)                                          # dfx_tc_assign: rows of the duplicated centroid overflow (G = 6 < 48)
+    st = g.get_state()
+    assert np.array_equal(st["list_off"], o.list_off) and np.array_equal(st["ids"], o.ids)
+    xq = np.concatenate([cent[cols[0]][None] + 0.01 * rs.randn(40, d), xb[300:340]]).astype(np.float32)
+    for nprobe in (1, 4, 20, 40):                      # 40 > 32: the rerank_kernel<2> branch
+        g.nprobe = nprobe; o.nprobe = nprobe
+        Do, Io = o.search(xq, 10)
+        for mode in (2, 1, 0):
+            g.set_param("tc_screen_mode", mode)
+            _assert_same(*g.search(xq, 10), Do, Io, f"duplicate centroids nprobe={nprobe} mode={mode}")
+            assert g.last_stats()["ndis"] == o.last_ndis
+    # (b) flat search: 64 copies of one row spread over 64 groups, k = 10 (G = 18 groups kept)
+    for metric in (IP, L2):
+        xf = rs.randn(_sz(8192, 4096), d).astype(np.float32)
+        fc = 32 * np.arange(64) + (31 - np.arange(64) % 32)
+        xf[fc] = xf[fc[0]]
+        gf = E.GpuIndex(E.KIND_FLAT, d, metric)
+        gf.add(xf)
+        qf = np.concatenate([xf[fc[0]][None] * 1.0 + 0.001 * rs.randn(8, d), rs.randn(8, d)]).astype(np.float32)
+        Do, Io = O.flat_search(metric, xf, qf, 10)
+        for mode in (2, 1, 0):
+            gf.set_param("tc_screen_mode", mode)
+            _assert_same(*gf.search(qf, 10), Do, Io, f"duplicate rows flat metric={metric} mode={mode}")
+
+
+def test_tensor_core_auto_precision_follows_the_data():
+    """tc_screen_mode 0 (AUTO): a shard starts with the PRECISE screening (fp16 hi/lo split, three
+    MMAs) and moves to FAST (one MMA) only after a launch whose statistics say that FAST's wider
+    tolerance would not overflow the kept groups; on data whose norms dwarf the gaps between
+    neighbouring centroids it stays PRECISE.  Results are the oracle's either way."""
+    from oracle import oracle as O
+
+    E = _engine()
+    rs = np.random.RandomState(23)
+    d, nlist, n = 64, 1024, _sz(30_000, 12_000)
+    A = np.linalg.qr(rs.randn(d, 6))[0].astype(np.float32)
+    for offset, expect_fast in ((0.0, 1.0), (300.0, 0.0)):
+        xb = (rs.randn(n, 6).astype(np.float32) @ A.T + offset).astype(np.float32)
+        g = E.GpuIndex(E.KIND_IVF_FLAT, d, L2, nlist=nlist)
+        g.set_param("kmeans_niter", 2)
+        g.train(xb[: n // 2])
+        g.add(xb)
+        o = O.make_index("ivf_flat", d, metric=L2, nlist=nlist)
+        o.set_state(g.get_state())
+        g.nprobe = 8; o.nprobe = 8
+        xq = xb[:256] + 0.01 * rs.randn(256, d).astype(np.float32)
+        Do, Io = o.search(xq, 10)
+        assert g.get_param("tc_fast") == 0.0                      # AUTO starts PRECISE
+        for it in range(3):
+            _assert_same(*g.search(xq, 10), Do, Io, f"auto precision offset={offset} launch {it}")
+        assert g.get_param("tc_stat_rows") == 256.0
+        assert g.get_param("tc_fast") == expect_fast, (offset, g.get_param("tc_stat_fast_would"))
+        if not expect_fast:
+            assert g.get_param("tc_stat_fast_would") > 4
 
 
 def test_tensor_core_assign_matches_oracle():
@@ -366,7 +452,12 @@ def test_tensor_core_assign_matches_oracle():
     g = E.GpuIndex(E.KIND_IVF_PQ, d, L2, nlist=nlist, pq_m=M)
     g.set_param("kmeans_niter", _sz(6, 2))
     g.train(xb[:_sz(40000, 3000)])
-    g.add(xb)
+    third = n // 3
+    g.add(xb[:third])                       # AUTO: a PRECISE probe chunk, then by its statistics
+    g.set_param("tc_screen_mode", 1)
+    g.add(xb[third:2 * third])              # FAST
+    g.set_param("tc_screen_mode", 2)
+    g.add(xb[2 * third:])                   # PRECISE
     st = g.get_state()
     o = O.OracleIVFPQ(d, nlist, M, 8, coarse_metric=L2)
     o.centroids, o.codebooks, o.is_trained = st["centroids"], st["codebooks"], True
@@ -487,10 +578,12 @@ def test_flat_tensor_core_path_matches_oracle(metric):
     for k in (1, 10, 33, 100):
         Do, Io = o.search(xq, k)
         g.set_param("flat_tensor_cores", 1)
-        _assert_same(*g.search(xq, k), Do, Io, f"flat TC k={k}")
+        for mode in (2, 1, 0):
+            g.set_param("tc_screen_mode", mode)
+            _assert_same(*g.search(xq, k), Do, Io, f"flat TC k={k} mode={mode}")
         g.set_param("flat_tensor_cores", 0)
         _assert_same(*g.search(xq, k), Do, Io, f"flat GEMM k={k}")
-    g.add(xb[n // 2:]); o.add(xb[n // 2:])            # the bf16 planes must follow
+    g.add(xb[n // 2:]); o.add(xb[n // 2:])            # the fp16 copy must follow
     g.set_param("flat_tensor_cores", 1)
     _assert_same(*g.search(xq, 10), *o.search(xq, 10), "flat TC after add")
     _assert_same(*g.search(xq[:1], 5), *o.search(xq[:1], 5), "flat TC nq=1")
