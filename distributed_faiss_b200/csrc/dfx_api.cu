@@ -132,6 +132,12 @@ int dfx_set_param(dfx_index* idx, const char* name, double value) {
         idx->tc_mode = (int)value;
         idx->tc_fast = value == 1;
         idx->tc_stat_pending = false;
+        idx->tc_acc_rows = idx->tc_acc_bad = 0;
+    }
+    else if (n == "tc_auto_window") {
+        DFX_REQUIRE(value >= 1 && value <= (double)(1 << 30), "tc_auto_window must be 1 .. 2^30 rows");
+        idx->tc_auto_window = (int64_t)value;
+        idx->tc_acc_rows = idx->tc_acc_bad = 0;
     }
     else if (n == "il2_threads") {
         DFX_REQUIRE(value == 0 || value == 256 || value == 512, "il2_threads must be 0 (default), 256 or 512");
@@ -159,6 +165,7 @@ int dfx_get_param(dfx_index* idx, const char* name, double* value) {
     else if (n == "tensor_cores") *value = idx->tc_enabled;
     else if (n == "tc_screen_mode") *value = idx->tc_mode;
     else if (n == "tc_fast") *value = idx->tc_fast;
+    else if (n == "tc_auto_window") *value = (double)idx->tc_auto_window;
     else if (n == "tc_cmax2") *value = idx->tc_cmax2;
     else if (n == "tc_stat_rows") *value = (double)idx->tc_last_rows;
     else if (n == "tc_stat_overflow") *value = (double)idx->tc_last_overflow;

@@ -45,7 +45,7 @@ struct dfx_index {
     bool cbT_valid = false;
 
     // tensor-core coarse quantizer (dfx_tc.cu): fp16 copies (1 or 2 planes) and screening workspace
-    DevBuf tc_cent, tc_cent_tmp, tc_q, tc_qmult, tc_gmin, tc_gmin2, tc_gargc, tc_groups, tc_cand, tc_qn, tc_amb, tc_ovf;
+    DevBuf tc_cent, tc_cent_tmp, tc_q, tc_qmult, tc_gmin, tc_tmin, tc_gmin2, tc_gargc, tc_groups, tc_cand, tc_qn, tc_amb, tc_ovf;
     float tc_cmax2 = 0.f;
     float tc_cscale = 1.f;      // power-of-two scale of the fp16 copy tc_cent
     // screening precision (dfx_tc.cu): tc_mode 0 = AUTO, 1 = FAST (one fp16 MMA per k-step),
@@ -59,6 +59,8 @@ struct dfx_index {
     bool tc_stat_pending = false, tc_stat_fast = false;
     int64_t tc_stat_rows = 0;
     int64_t tc_last_rows = 0, tc_last_overflow = 0, tc_last_fast_would = 0;  // of the last launch polled
+    int64_t tc_auto_window = 16384;            // AUTO: rows observed before PRECISE may become FAST
+    int64_t tc_acc_rows = 0, tc_acc_bad = 0;   // AUTO: rows / rows that (would) overflow since the last decision
     bool tc_ready = false;
     bool tc_enabled = true;
     int rows_inflight = 0;      // vectors in flight per warp of scan_rows_kernel: 0 = by row size, else 4 / 8

@@ -245,7 +245,7 @@ f16_rows_kernel(const float* __restrict__ x, int64_t n, int64_t n_pad, int d, in
 // overflow fallback, the drivers) is the product code.
 static void emu_tc_screen(const __half* qh, const float* qmult, int64_t nq, int64_t nq_pad, const __half* ch,
                           int64_t nlist, int64_t nl_pad, int d, int npl, const float* cnorm, int metric, float* gmin,
-                          float* gmin2, uint8_t* gargc, int ng) {
+                          float* gmin2, uint8_t* gargc, float* tmin, int ng) {
     const float big = 3.0e38f;
     std::vector<float> cf((size_t)npl * nl_pad * d), qf((size_t)npl * d);
     for (size_t i = 0; i < cf.size(); i++) cf[i] = __half2float(ch[i]);
@@ -280,6 +280,10 @@ static void emu_tc_screen(const __half* qh, const float* qmult, int64_t nq, int6
             gmin2[row * ng + g] = m2;
             gargc[row * ng + g] = (uint8_t)(u1 & 31u);
         }
+        for (int t = 0; t < ng / 4; t++) {  // the minimum of every tile of 4 groups
+            const float* gm = gmin + row * ng + 4 * t;
+            tmin[row * (ng / 4) + t] = fminf(fminf(gm[0], gm[1]), fminf(gm[2], gm[3]));
+        }
     }
 }
 #else
@@ -293,7 +297,7 @@ __global__ void __launch_bounds__(tc::THREADS, (KT != 0 && NPL == 1) ? 2 : 1)
 tc_coarse_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmC, int nq,
                  int nq_pad, int nlist, int nl_pad, int katoms_rt, const float* __restrict__ cnorm,
                  const float* __restrict__ qmult, int ctiles_per_cta, float* __restrict__ gmin,
-                 float* __restrict__ gmin2, uint8_t* __restrict__ gargc, int ng) {
+                 float* __restrict__ gmin2, uint8_t* __restrict__ gargc, float* __restrict__ tmin, int ng) {
     using namespace tc;
     constexpr bool RES = KT != 0;
     const int KATOMS = KT ? KT : katoms_rt;
@@ -467,6 +471,8 @@ tc_coarse_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                 *reinterpret_cast<float4*>(gmin + o) = make_float4(gm[0], gm[1], gm[2], gm[3]);
                 *reinterpret_cast<float4*>(gmin2 + o) = make_float4(gm2[0], gm2[1], gm2[2], gm2[3]);
                 *reinterpret_cast<uint32_t*>(gargc + o) = ga;
+                // the tile's minimum: the first level of the group selection (topg_collect_kernel)
+                tmin[grow * (ng >> 2) + (col0 >> 7)] = fminf(fminf(gm[0], gm[1]), fminf(gm[2], gm[3]));
             }
         }
     }
@@ -558,24 +564,54 @@ __device__ __forceinline__ float screen_threshold(const int32_t* __restrict__ gr
 }
 
 // The G (<= 32) smallest group minima of a row, ascending by (value, group): one warp per row.
-//   1. every lane takes the minimum of its ng/32 values; the G-th smallest of those 32 lane
+//   1. every lane takes the minimum of its n/32 values; the G-th smallest of those 32 lane
 //      minima, B, bounds the answer from above (G different lanes hold a value <= B);
 //   2. the values <= B are collected (a few dozen at most in practice) into a per-warp buffer;
-//   3. the buffer is bitonic-sorted by the warp and the first G entries are written.
+//   3. the buffer is bitonic-sorted by the warp and the first G entries are kept.
 // Exact for any input; if more than CAP values are <= B (massive ties) the row falls back to
-// G rounds of warp arg-min.  ~10x fewer instructions than G x ng compare rounds.
+// G rounds of warp arg-min.  ~10x fewer instructions than G x n compare rounds.
+// Two levels (fine != nullptr): `coarse` holds the minimum of every FINE_PER = 4 consecutive
+// groups (one 128-column tile of the screening kernel, written by its epilogue) -- steps 1-3 run
+// on the n / 4 tile minima, then the 4 G groups of the G smallest tiles are sorted and the first
+// G kept.  The G smallest groups always lie in the G smallest tiles: a group g outside them
+// would have G tiles, each holding a group with (minimum, index) below g's, before it.
+template <int CAP>
+__device__ __forceinline__ void warp_sort_buf(uint64_t* buf, int cnt, int lane, int& P) {
+    P = 32;
+    while (P < cnt) P <<= 1;
+    for (int e = cnt + lane; e < P; e += 32) buf[e] = DFX_COMP_NONE;
+    __syncwarp();
+    for (int size = 2; size <= P; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int i = lane; i < (P >> 1); i += 32) {
+                const int pos = 2 * i - (i & (stride - 1));
+                const int partner = pos + stride;
+                const bool up = ((pos & size) == 0);
+                const uint64_t a = buf[pos], bb = buf[partner];
+                if ((a > bb) == up) {
+                    buf[pos] = bb;
+                    buf[partner] = a;
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
 template <int CAP>
 __global__ void __launch_bounds__(256)
-topg_collect_kernel(const float* __restrict__ gmin, int64_t nq, int ng, int G, int32_t* __restrict__ groups) {
+topg_collect_kernel(const float* __restrict__ coarse, int64_t nq, int n, int G, const float* __restrict__ fine,
+                    int n_fine, int32_t* __restrict__ groups) {
+    constexpr int FINE_PER = 4;
+    static_assert(CAP >= 32 * FINE_PER, "the expansion of 32 tiles must fit the buffer");
     __shared__ uint64_t s_buf[8][CAP];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t row = (int64_t)blockIdx.x * 8 + warp;
     if (row >= nq) return;
-    const float* g = gmin + row * ng;
+    const float* g = coarse + row * n;
     uint64_t* buf = s_buf[warp];
     // 1. lane minima -> bound
     uint64_t lmin = DFX_COMP_NONE;
-    for (int j = lane; j < ng; j += 32) {
+    for (int j = lane; j < n; j += 32) {
         const uint64_t c = dfx_comp(g[j], (uint32_t)j);
         lmin = c < lmin ? c : lmin;
     }
@@ -597,9 +633,9 @@ topg_collect_kernel(const float* __restrict__ gmin, int64_t nq, int ng, int G, i
     // 2. collect everything <= bound
     int cnt = 0;
     bool overflow = false;
-    for (int j0 = 0; j0 < ng; j0 += 32) {
+    for (int j0 = 0; j0 < n; j0 += 32) {
         const int j = j0 + lane;
-        const uint64_t c = (j < ng) ? dfx_comp(g[j], (uint32_t)j) : DFX_COMP_NONE;
+        const uint64_t c = (j < n) ? dfx_comp(g[j], (uint32_t)j) : DFX_COMP_NONE;
         const bool want = c <= bound && c != DFX_COMP_NONE;
         const unsigned mask = __ballot_sync(0xffffffffu, want);
         if (mask) {
@@ -609,49 +645,46 @@ topg_collect_kernel(const float* __restrict__ gmin, int64_t nq, int ng, int G, i
             if (cnt > CAP) overflow = true;
         }
     }
+    int P = 32;
     if (!overflow) {
-        // 3. sort the candidates
-        int P = 32;
-        while (P < cnt) P <<= 1;
-        for (int e = cnt + lane; e < P; e += 32) buf[e] = DFX_COMP_NONE;
-        __syncwarp();
-        for (int size = 2; size <= P; size <<= 1) {
-            for (int stride = size >> 1; stride > 0; stride >>= 1) {
-                for (int i = lane; i < (P >> 1); i += 32) {
-                    const int pos = 2 * i - (i & (stride - 1));
-                    const int partner = pos + stride;
-                    const bool up = ((pos & size) == 0);
-                    const uint64_t a = buf[pos], bb = buf[partner];
-                    if ((a > bb) == up) {
-                        buf[pos] = bb;
-                        buf[partner] = a;
-                    }
-                }
-                __syncwarp();
+        warp_sort_buf<CAP>(buf, cnt, lane, P);  // 3. sort the candidates
+    } else {
+        // fallback: G rounds of "smallest composite above the previous pick", left in buf[0..G)
+        uint64_t prev = 0;
+        for (int r = 0; r < G; r++) {
+            uint64_t best = DFX_COMP_NONE;
+            for (int j = lane; j < n; j += 32) {
+                const uint64_t c = dfx_comp(g[j], (uint32_t)j);
+                if ((r == 0 || c > prev) && c < best) best = c;
             }
-        }
-        for (int r = lane; r < G; r += 32) {
-            const uint64_t c = (r < P) ? buf[r] : DFX_COMP_NONE;
-            groups[row * G + r] = (c == DFX_COMP_NONE) ? -1 : (int32_t)(uint32_t)c;
-        }
-        return;
-    }
-    // fallback: G rounds of "smallest composite above the previous pick"
-    uint64_t prev = 0;
-    for (int r = 0; r < G; r++) {
-        uint64_t best = DFX_COMP_NONE;
-        for (int j = lane; j < ng; j += 32) {
-            const uint64_t c = dfx_comp(g[j], (uint32_t)j);
-            if ((r == 0 || c > prev) && c < best) best = c;
-        }
 #pragma unroll
-        for (int off = 16; off >= 1; off >>= 1) {
-            const uint64_t o = __shfl_xor_sync(0xffffffffu, best, off);
-            best = o < best ? o : best;
+            for (int off = 16; off >= 1; off >>= 1) {
+                const uint64_t o = __shfl_xor_sync(0xffffffffu, best, off);
+                best = o < best ? o : best;
+            }
+            if (lane == 0) buf[r] = best;
+            prev = best;
+            if (best == DFX_COMP_NONE) prev = DFX_COMP_NONE - 1;
         }
-        if (lane == 0) groups[row * G + r] = (best == DFX_COMP_NONE) ? -1 : (int32_t)(uint32_t)best;
-        prev = best;
-        if (best == DFX_COMP_NONE) prev = DFX_COMP_NONE - 1;
+        __syncwarp();
+    }
+    if (fine) {  // second level: the groups of the G smallest tiles
+        const uint64_t tc_ = (lane < G && (overflow || lane < P)) ? buf[lane] : DFX_COMP_NONE;
+        __syncwarp();
+        const float* f = fine + row * n_fine;
+#pragma unroll
+        for (int j = 0; j < FINE_PER; j++) {
+            const int64_t gi = (int64_t)(uint32_t)tc_ * FINE_PER + j;
+            buf[lane * FINE_PER + j] =
+                (tc_ != DFX_COMP_NONE && gi < n_fine) ? dfx_comp(f[gi], (uint32_t)gi) : DFX_COMP_NONE;
+        }
+        __syncwarp();
+        warp_sort_buf<CAP>(buf, 32 * FINE_PER, lane, P);
+        overflow = false;
+    }
+    for (int r = lane; r < G; r += 32) {
+        const uint64_t c = (overflow || r < P) ? buf[r] : DFX_COMP_NONE;
+        groups[row * G + r] = (c == DFX_COMP_NONE) ? -1 : (int32_t)(uint32_t)c;
     }
 }
 
@@ -1000,6 +1033,7 @@ void dfx_tc_prepare_centroids(dfx_index* idx, cudaStream_t st) {
     idx->tc_ready = true;
     if (idx->tc_mode == 0) idx->tc_fast = false;  // AUTO: a new table starts PRECISE
     idx->tc_stat_pending = false;
+    idx->tc_acc_rows = idx->tc_acc_bad = 0;
 }
 
 // ---- AUTO precision: statistics of a past launch come back through pinned memory, no sync
@@ -1011,21 +1045,35 @@ static bool tc_stream_capturing(cudaStream_t st) {
     }
     return cs != cudaStreamCaptureStatusNone;
 }
-// AUTO rule: PRECISE -> FAST when at most 1/256 of a launch's rows would overflow under FAST's
-// tolerance; FAST -> PRECISE when more than 1/64 of a launch's rows overflowed.  Either way the
-// results are exact; only the cost moves.  A switch bumps `generation` (captured graphs are stale).
+// AUTO rule.  A row that overflows costs an exact pass over ALL columns by one CTA (milliseconds
+// at nlist = 65 536), more than FAST saves on a whole launch, so FAST is only worth it where
+// overflows practically never happen: PRECISE -> FAST after at least 16 384 observed rows none of
+// which would have overflowed under FAST's tolerance; FAST -> PRECISE as soon as more than one row
+// in 16 384 did overflow.  Counts accumulate across launches (a batch of one query says nothing
+// on its own).  Either way the results are exact; only the cost moves.  A switch bumps
+// `generation` (captured graphs are stale).
 static void tc_auto_update(dfx_index* idx, bool was_fast, int64_t rows, int64_t overflowed, int64_t fast_would) {
-    if (idx->tc_mode != 0 || rows <= 0) return;
+    if (idx->tc_mode != 0 || rows <= 0 || was_fast != idx->tc_fast) return;
+    idx->tc_acc_rows += rows;
+    idx->tc_acc_bad += was_fast ? overflowed : fast_would;
     bool fast = idx->tc_fast;
-    if (was_fast && overflowed * 64 > rows) fast = false;
-    else if (!was_fast && fast_would * 256 <= rows) fast = true;
+    const int64_t window = idx->tc_auto_window;  // 16 384 rows unless dfx_set_param("tc_auto_window") says otherwise
+    if (!fast && idx->tc_acc_rows >= window) {
+        fast = idx->tc_acc_bad == 0;
+        idx->tc_acc_rows = idx->tc_acc_bad = 0;
+    } else if (fast && idx->tc_acc_bad > 0 && idx->tc_acc_bad * window > idx->tc_acc_rows) {
+        fast = false;
+        idx->tc_acc_rows = idx->tc_acc_bad = 0;
+    } else if (fast && idx->tc_acc_rows >= (1 << 20)) {
+        idx->tc_acc_rows = idx->tc_acc_bad = 0;  // a fresh window
+    }
     if (fast != idx->tc_fast) {
         idx->tc_fast = fast;
         idx->generation++;
     }
 }
-static void tc_stats_poll(dfx_index* idx) {  // before choosing the precision of a launch
-    if (!idx->tc_stat_pending) return;
+static void tc_stats_poll(dfx_index* idx, cudaStream_t st) {  // before choosing the precision of a launch
+    if (!idx->tc_stat_pending || tc_stream_capturing(st)) return;  // (no event queries inside a capture)
     if (cudaEventQuery(idx->tc_stat_ev) != cudaSuccess) {
         cudaGetLastError();  // not ready yet: keep the current precision
         return;
@@ -1039,7 +1087,7 @@ static void tc_stats_poll(dfx_index* idx) {  // before choosing the precision of
 void dfx_tc_stats_sync(dfx_index* idx) {
     if (!idx->tc_stat_pending) return;
     cudaEventSynchronize(idx->tc_stat_ev);
-    tc_stats_poll(idx);
+    tc_stats_poll(idx, nullptr);
 }
 static void tc_stats_post(dfx_index* idx, const int32_t* ovf, int64_t rows, bool fast, cudaStream_t st) {
     if (idx->tc_mode != 0 || idx->tc_stat_pending || tc_stream_capturing(st)) return;
@@ -1064,7 +1112,7 @@ static ScreenTol tc_tol(const dfx_index* idx, int d, bool fast) {
 // (npl planes used; the table must hold at least npl); also leaves |q|^2 in idx->tc_qn
 static void tc_screen(dfx_index* idx, int d, const float* d_x, int64_t nq, const void* table_h, float table_scale,
                       int npl, const float* cnorm, int64_t nlist, int metric, float* gmin, float* gmin2,
-                      uint8_t* gargc, cudaStream_t st) {
+                      uint8_t* gargc, float* tmin, cudaStream_t st) {
     using namespace tc;
     const int64_t nl_pad = dfx_ceil_div(nlist, TILE) * TILE;
     const int64_t nq_pad = dfx_ceil_div(nq, TILE) * TILE;
@@ -1076,7 +1124,7 @@ static void tc_screen(dfx_index* idx, int d, const float* d_x, int64_t nq, const
                (float*)nullptr);
 #ifdef DFX_EMU
     emu_tc_screen(idx->tc_q.as<__half>(), idx->tc_qmult.as<float>(), nq, nq_pad, static_cast<const __half*>(table_h),
-                  nlist, nl_pad, d, npl, cnorm, metric, gmin, gmin2, gargc, ng);
+                  nlist, nl_pad, d, npl, cnorm, metric, gmin, gmin2, gargc, tmin, ng);
     return;
 #else
     CUtensorMap tmQ, tmC;
@@ -1115,7 +1163,7 @@ static void tc_screen(dfx_index* idx, int d, const float* d_x, int64_t nq, const
         auto kern = tc_coarse_kernel<KT_, MT, NP>;                                                       \
         DFX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
         DFX_LAUNCH(kern, grid, THREADS, smem, st, tmQ, tmC, (int)nq, (int)nq_pad, (int)nlist, (int)nl_pad, katoms, \
-                   cnorm, idx->tc_qmult.as<float>(), per, gmin, gmin2, gargc, ng);                       \
+                   cnorm, idx->tc_qmult.as<float>(), per, gmin, gmin2, gargc, tmin, ng);                 \
     } while (0)
 #define DFX_TC_LAUNCH_M(KT_, NP)                                          \
     do {                                                                  \
@@ -1136,6 +1184,22 @@ static void tc_screen(dfx_index* idx, int d, const float* d_x, int64_t nq, const
 #undef DFX_TC_LAUNCH_M
 #undef DFX_TC_LAUNCH
 #endif  // DFX_EMU
+}
+
+// the G groups of every row with the smallest minima, ascending: two-level warp selection for
+// G <= 32 (tile minima first), the generic radix select otherwise
+static void tc_select_groups(const float* gmin, const float* tmin, int64_t nrows, int ng, int G, int32_t* groups,
+                             cudaStream_t st) {
+    if (G <= 32 && ng >= 128) {
+        auto tk = topg_collect_kernel<256>;
+        DFX_LAUNCH(tk, (unsigned)dfx_ceil_div(nrows, 8), 256, 0, st, tmin, nrows, ng / 4, G, gmin, ng, groups);
+    } else if (G <= 32 && ng >= 32) {
+        auto tk = topg_collect_kernel<256>;
+        DFX_LAUNCH(tk, (unsigned)dfx_ceil_div(nrows, 8), 256, 0, st, gmin, nrows, ng, G, (const float*)nullptr, 0,
+                   groups);
+    } else {
+        dfx_launch_select_cols(gmin, nrows, ng, ng, G, 0, groups, nullptr, nullptr, 0, st);
+    }
 }
 
 // the overflow record of a decide launch: [overflow rows, FAST-would-overflow rows, row list ...]
@@ -1160,13 +1224,15 @@ void dfx_tc_coarse_search(dfx_index* idx, const float* d_x, int64_t nq, int npro
     idx->tc_gmin2.reserve((size_t)qmax * ng * 4);
     idx->tc_gargc.reserve((size_t)qmax * ng);
     idx->tc_groups.reserve((size_t)qmax * G * 4);
+    idx->tc_tmin.reserve((size_t)qmax * (ng / 4 + 1) * 4);
+    float* tmin = idx->tc_tmin.as<float>();
     const float* cent = idx->centroids.as<float>();
     const float* cnorm = idx->cnorm.as<float>();
     float* gmin = idx->tc_gmin.as<float>();
     float* gmin2 = idx->tc_gmin2.as<float>();
     uint8_t* gargc = idx->tc_gargc.as<uint8_t>();
     int32_t* groups = idx->tc_groups.as<int32_t>();
-    tc_stats_poll(idx);
+    tc_stats_poll(idx, st);
     const bool fast = idx->tc_fast;
     const ScreenTol tol = tc_tol(idx, d, fast);
     for (int64_t q0 = 0; q0 < nq; q0 += QC) {
@@ -1174,13 +1240,8 @@ void dfx_tc_coarse_search(dfx_index* idx, const float* d_x, int64_t nq, int npro
         const float* xq = d_x + q0 * d;
         int32_t* kq = keys + q0 * nprobe;
         tc_screen(idx, d, xq, qc, idx->tc_cent.p, idx->tc_cscale, fast ? 1 : 2, cnorm, nlist, metric, gmin, gmin2,
-                  gargc, st);
-        if (G <= 32 && ng >= 32) {
-            auto tk = topg_collect_kernel<256>;
-            DFX_LAUNCH(tk, (unsigned)dfx_ceil_div(qc, 8), 256, 0, st, gmin, qc, ng, G, groups);
-        } else {
-            dfx_launch_select_cols(gmin, qc, ng, ng, G, 0, groups, nullptr, nullptr, 0, st);
-        }
+                  gargc, tmin, st);
+        tc_select_groups(gmin, tmin, qc, ng, G, groups, st);
         int32_t* ovf = tc_ovf_reset(idx, qc, st);
         const int P_cand = dfx_next_pow2(G * 32 < 32 ? 32 : G * 32);
         if (nprobe <= 32 && G <= 64 && d % 4 == 0) {  // warp per query
@@ -1237,8 +1298,9 @@ int dfx_tc_flat_candidates(dfx_index* idx, const float* d_x, int64_t nq, int k, 
         idx->tc_flat_rows = N;
         if (idx->tc_mode == 0) idx->tc_fast = false;  // AUTO: new rows start PRECISE
         idx->tc_stat_pending = false;
+        idx->tc_acc_rows = idx->tc_acc_bad = 0;
     }
-    tc_stats_poll(idx);
+    tc_stats_poll(idx, st);
     const bool fast = idx->tc_fast;
     const ScreenTol tol = tc_tol(idx, d, fast);
     int G = k + 8;
@@ -1249,16 +1311,11 @@ int dfx_tc_flat_candidates(dfx_index* idx, const float* d_x, int64_t nq, int k, 
     idx->tc_gargc.reserve((size_t)nq * ng);
     idx->tc_groups.reserve((size_t)nq * G * 4);
     idx->tc_cand.reserve((size_t)nq * ncand * 8);
+    idx->tc_tmin.reserve((size_t)nq * (ng / 4 + 1) * 4);
     tc_screen(idx, d, d_x, nq, idx->tc_cent.p, idx->tc_cscale, fast ? 1 : 2, idx->xnorm.as<float>(), N, metric,
-              idx->tc_gmin.as<float>(), idx->tc_gmin2.as<float>(), idx->tc_gargc.as<uint8_t>(), st);
-    if (G <= 32 && ng >= 32) {
-        auto tk = topg_collect_kernel<256>;
-        DFX_LAUNCH(tk, (unsigned)dfx_ceil_div(nq, 8), 256, 0, st, idx->tc_gmin.as<float>(), nq, ng, G,
-                   idx->tc_groups.as<int32_t>());
-    } else {
-        dfx_launch_select_cols(idx->tc_gmin.as<float>(), nq, ng, ng, G, 0, idx->tc_groups.as<int32_t>(), nullptr,
-                               nullptr, 0, st);
-    }
+              idx->tc_gmin.as<float>(), idx->tc_gmin2.as<float>(), idx->tc_gargc.as<uint8_t>(),
+              idx->tc_tmin.as<float>(), st);
+    tc_select_groups(idx->tc_gmin.as<float>(), idx->tc_tmin.as<float>(), nq, ng, G, idx->tc_groups.as<int32_t>(), st);
     int32_t* ovf = tc_ovf_reset(idx, nq, st);
     auto kern = rerank_kernel<0>;
     DFX_LAUNCH(kern, (unsigned)nq, 128, (size_t)d * 4, st, d_x, d, idx->payload.as<float>(), idx->xnorm.as<float>(), N,
@@ -1287,6 +1344,7 @@ void dfx_tc_assign(dfx_index* idx, int d, const float* d_cent, const float* d_cn
     idx->tc_gmin2.reserve((size_t)rmax * ng * 4);
     idx->tc_gargc.reserve((size_t)rmax * ng);
     idx->tc_groups.reserve((size_t)rmax * G * 4);
+    idx->tc_tmin.reserve((size_t)rmax * (ng / 4 + 1) * 4);
     idx->tc_qn.reserve((size_t)rmax * 4);
     idx->tc_amb.reserve((size_t)(rmax + 1) * 4);
     // fp16 copy of this centroid table (k-means changes it every iteration; converting is cheap).
@@ -1295,25 +1353,22 @@ void dfx_tc_assign(dfx_index* idx, int d, const float* d_cent, const float* d_cn
     const float cmax2 = max_norm2(idx, d_cnorm, nlist, st);
     const float cscale = tc_prepare_table(d_cent, nlist, d, cmax2, 2, idx->tc_cent_tmp, st);
     bool fast = idx->tc_mode == 1;
+    int64_t acc_rows = 0, acc_bad = 0;
     for (int64_t r0 = 0, rc = 0; r0 < n; r0 += rc) {
-        // the first AUTO chunk is a small PRECISE probe, so that most of the rows run at the
-        // precision their statistics call for
-        rc = (idx->tc_mode == 0 && r0 == 0) ? std::min<int64_t>(n, 64 * tc::TILE) : std::min(RC, n - r0);
+        // the first AUTO chunk is a small PRECISE probe (16 384 rows), so that most of the rows run
+        // at the precision their statistics call for
+        rc = (idx->tc_mode == 0 && r0 == 0) ? std::min<int64_t>(n, dfx_ceil_div(idx->tc_auto_window, tc::TILE) * tc::TILE)
+                                            : std::min(RC, n - r0);
         const float* xr = d_x + r0 * d;
         ScreenTol tol;
         tol.rel = screen_tol_rel(d, fast);
         tol.rel_fast = 0.f;  // counted once per row by assign_resolve_kernel
         const float rel_fast = (!fast && idx->tc_mode == 0) ? screen_tol_rel(d, true) : 0.f;
         tc_screen(idx, d, xr, rc, idx->tc_cent_tmp.p, cscale, fast ? 1 : 2, d_cnorm, nlist, metric,
-                  idx->tc_gmin.as<float>(), idx->tc_gmin2.as<float>(), idx->tc_gargc.as<uint8_t>(), st);
-        if (ng >= 32) {
-            auto tk = topg_collect_kernel<256>;
-            DFX_LAUNCH(tk, (unsigned)dfx_ceil_div(rc, 8), 256, 0, st, idx->tc_gmin.as<float>(), rc, ng, G,
-                       idx->tc_groups.as<int32_t>());
-        } else {
-            dfx_launch_select_cols(idx->tc_gmin.as<float>(), rc, ng, ng, G, 0, idx->tc_groups.as<int32_t>(), nullptr,
-                                   nullptr, 0, st);
-        }
+                  idx->tc_gmin.as<float>(), idx->tc_gmin2.as<float>(), idx->tc_gargc.as<uint8_t>(),
+                  idx->tc_tmin.as<float>(), st);
+        tc_select_groups(idx->tc_gmin.as<float>(), idx->tc_tmin.as<float>(), rc, ng, G, idx->tc_groups.as<int32_t>(),
+                         st);
         dfx_launch_row_norms(xr, rc, d, idx->tc_qn.as<float>(), st);
         int32_t* amb_count = idx->tc_amb.as<int32_t>();
         int32_t* amb_rows = amb_count + 1;
@@ -1330,12 +1385,19 @@ void dfx_tc_assign(dfx_index* idx, int d, const float* d_cent, const float* d_cn
                    idx->tc_gargc.as<uint8_t>(), ng, cmax2, tol, (uint64_t*)nullptr, d_assign + r0,
                    (const int32_t*)amb_rows, (const int32_t*)amb_count, rc, (int32_t*)nullptr, ovf);
         launch_exact_rows(xr, d_cent, d_cnorm, nlist, d, metric, ovf, rc, 1, 1, nullptr, d_assign + r0, nullptr, st);
-        if (idx->tc_mode == 0 && r0 + rc < n) {  // AUTO: the next chunk's precision
+        if (idx->tc_mode == 0 && r0 + rc < n) {  // AUTO: the next chunk's precision (rule of tc_auto_update)
             int32_t h[2] = {0, 0};
             DFX_CUDA(cudaMemcpyAsync(h, ovf, 8, cudaMemcpyDeviceToHost, st));
             DFX_CUDA(cudaStreamSynchronize(st));
-            if (fast && (int64_t)h[0] * 64 > rc) fast = false;
-            else if (!fast && (int64_t)h[1] * 256 <= rc) fast = true;
+            acc_rows += rc;
+            acc_bad += fast ? h[0] : h[1];
+            if (!fast && acc_rows >= idx->tc_auto_window) {
+                fast = acc_bad == 0;
+                acc_rows = acc_bad = 0;
+            } else if (fast && acc_bad > 0 && acc_bad * idx->tc_auto_window > acc_rows) {
+                fast = false;
+                acc_rows = acc_bad = 0;
+            }
         }
     }
 }

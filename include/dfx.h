@@ -73,8 +73,10 @@ int dfx_add_dev(dfx_index *idx, int64_t n, const float *d_x, void *stream);
  * "tensor_cores" (1): 0 forces the plain fp32 FFMA coarse quantizer instead of the tcgen05
  *   screening path;
  * "tc_screen_mode" (0): precision of the tcgen05 screening: 0 = AUTO (starts PRECISE, moves to
- *   FAST once a launch shows FAST's wider tolerance would not overflow the kept groups, and back),
+ *   FAST once enough rows have shown that FAST's wider tolerance would not overflow the kept
+ *   groups, and back as soon as it does),
  *   1 = FAST (fp16 operands, one MMA per k-step), 2 = PRECISE (fp16 hi/lo split, three MMAs);
+ *   "tc_auto_window" (16384): rows AUTO observes before PRECISE may become FAST;
  * "flat_tensor_cores" (1): 0 runs FLAT searches through the FFMA GEMM instead of the tensor-core
  *   screening + exact re-rank;
  * "interleaved" (1): 0 keeps IVF-PQ (M = 32) codes row-major (one vector per lane, table from

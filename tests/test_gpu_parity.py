@@ -411,9 +411,10 @@ def test_tensor_core_near_tie_overflow_is_redone_exactly():
 
 def test_tensor_core_auto_precision_follows_the_data():
     """tc_screen_mode 0 (AUTO): a shard starts with the PRECISE screening (fp16 hi/lo split, three
-    MMAs) and moves to FAST (one MMA) only after a launch whose statistics say that FAST's wider
-    tolerance would not overflow the kept groups; on data whose norms dwarf the gaps between
-    neighbouring centroids it stays PRECISE.  Results are the oracle's either way."""
+    MMAs) and moves to FAST (one MMA) only after 16 384 observed rows none of which would have
+    overflowed the kept groups under FAST's wider tolerance (an overflowing row costs an exact
+    pass over all lists); on data whose norms dwarf the gaps between neighbouring centroids it
+    stays PRECISE.  Results are the oracle's either way."""
     from oracle import oracle as O
 
     E = _engine()
@@ -429,15 +430,21 @@ def test_tensor_core_auto_precision_follows_the_data():
         o = O.make_index("ivf_flat", d, metric=L2, nlist=nlist)
         o.set_state(g.get_state())
         g.nprobe = 8; o.nprobe = 8
-        xq = xb[:256] + 0.01 * rs.randn(256, d).astype(np.float32)
-        Do, Io = o.search(xq, 10)
+        nb = _sz(4096, 128)                                       # rows per launch
+        g.set_param("tc_auto_window", 4 * nb)                     # (default 16 384 = 4 launches of 4096)
+        xq = xb[:nb] + 0.01 * rs.randn(nb, d).astype(np.float32)
+        Do, Io = o.search(xq[:128], 10)
         assert g.get_param("tc_fast") == 0.0                      # AUTO starts PRECISE
-        for it in range(3):
-            _assert_same(*g.search(xq, 10), Do, Io, f"auto precision offset={offset} launch {it}")
-        assert g.get_param("tc_stat_rows") == 256.0
+        g.search(xq[:1], 10)                                      # a single row decides nothing
+        assert g.get_param("tc_fast") == 0.0
+        for it in range(5):                                       # more rows than the window
+            Dg, Ig = g.search(xq, 10)
+            _assert_same(Dg[:128], Ig[:128], Do, Io, f"auto precision offset={offset} launch {it}")
+        assert g.get_param("tc_stat_rows") == float(nb)
         assert g.get_param("tc_fast") == expect_fast, (offset, g.get_param("tc_stat_fast_would"))
         if not expect_fast:
-            assert g.get_param("tc_stat_fast_would") > 4
+            assert g.get_param("tc_stat_fast_would") > 0
+        _assert_same(*g.search(xq[:128], 10), Do, Io, f"auto precision offset={offset}, settled")
 
 
 def test_tensor_core_assign_matches_oracle():
