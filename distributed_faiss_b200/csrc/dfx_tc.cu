@@ -609,11 +609,33 @@ topg_collect_kernel(const float* __restrict__ coarse, int64_t nq, int n, int G, 
     if (row >= nq) return;
     const float* g = coarse + row * n;
     uint64_t* buf = s_buf[warp];
+    // (n <= 512, the usual case -- 65 536 lists = 512 tiles: the row is loaded ONCE, 16 independent
+    // loads per lane, and both passes run on registers; the loops below were bound by one L2
+    // latency per iteration)
+    constexpr int REGV = 16;
+    const bool in_regs = n <= 32 * REGV;
+    float rv[REGV];
+    if (in_regs) {
+#pragma unroll
+        for (int i = 0; i < REGV; i++) {
+            const int j = lane + 32 * i;
+            rv[i] = (j < n) ? g[j] : 0.f;
+        }
+    }
     // 1. lane minima -> bound
     uint64_t lmin = DFX_COMP_NONE;
-    for (int j = lane; j < n; j += 32) {
-        const uint64_t c = dfx_comp(g[j], (uint32_t)j);
-        lmin = c < lmin ? c : lmin;
+    if (in_regs) {
+#pragma unroll
+        for (int i = 0; i < REGV; i++) {
+            const int j = lane + 32 * i;
+            const uint64_t c = (j < n) ? dfx_comp(rv[i], (uint32_t)j) : DFX_COMP_NONE;
+            lmin = c < lmin ? c : lmin;
+        }
+    } else {
+        for (int j = lane; j < n; j += 32) {
+            const uint64_t c = dfx_comp(g[j], (uint32_t)j);
+            lmin = c < lmin ? c : lmin;
+        }
     }
     // bitonic sort of the 32 lane minima across the warp (ascending by lane)
     uint64_t x = lmin;
@@ -633,9 +655,16 @@ topg_collect_kernel(const float* __restrict__ coarse, int64_t nq, int n, int G, 
     // 2. collect everything <= bound
     int cnt = 0;
     bool overflow = false;
-    for (int j0 = 0; j0 < n; j0 += 32) {
+    for (int j0 = 0, it = 0; j0 < n; j0 += 32, it++) {
         const int j = j0 + lane;
-        const uint64_t c = (j < n) ? dfx_comp(g[j], (uint32_t)j) : DFX_COMP_NONE;
+        float gv = 0.f;
+        if (in_regs) {
+#pragma unroll
+            for (int i = 0; i < REGV; i++) gv = (i == it) ? rv[i] : gv;  // rv[it] without local memory
+        } else if (j < n) {
+            gv = g[j];
+        }
+        const uint64_t c = (j < n) ? dfx_comp(gv, (uint32_t)j) : DFX_COMP_NONE;
         const bool want = c <= bound && c != DFX_COMP_NONE;
         const unsigned mask = __ballot_sync(0xffffffffu, want);
         if (mask) {
@@ -738,7 +767,8 @@ rerank_kernel(const float* __restrict__ Q, int d, const float* __restrict__ cent
                 if (live && col < nlist) {
                     const float* x = cent + col * d;
                     float acc = 0.f;
-                    for (int k = 0; k < d; k += 4) {
+#pragma unroll 8
+                    for (int k = 0; k < d; k += 4) {  // (unrolled: 8 row loads in flight, same FMA chain)
                         const float4 xv = *reinterpret_cast<const float4*>(x + k);
                         acc = __fmaf_rn(s_q[k + 0], xv.x, acc);
                         acc = __fmaf_rn(s_q[k + 1], xv.y, acc);
@@ -807,6 +837,7 @@ rerank2_kernel(const float* __restrict__ Q, int d, const float* __restrict__ cen
     float* s_q = reinterpret_cast<float*>(rr2_smem) + (size_t)warp * dq;
     int32_t* s_cand = reinterpret_cast<int32_t*>(rr2_smem + (size_t)RR2_WARPS * dq * 4) + (size_t)warp * G * 32;
     float part = 0.f;
+#pragma unroll 4
     for (int i = lane; i < d; i += 32) {
         const float v = Q[row * d + i];
         s_q[i] = v;
@@ -861,7 +892,8 @@ rerank2_kernel(const float* __restrict__ Q, int d, const float* __restrict__ cen
             const int64_t col = s_cand[c0 + lane];
             const float* x = cent + col * d;
             float acc = 0.f;
-            for (int k = 0; k < d; k += 4) {
+#pragma unroll 8
+            for (int k = 0; k < d; k += 4) {  // (unrolled: 8 row loads in flight, same FMA chain)
                 const float4 xv = *reinterpret_cast<const float4*>(x + k);
                 acc = __fmaf_rn(s_q[k + 0], xv.x, acc);
                 acc = __fmaf_rn(s_q[k + 1], xv.y, acc);
