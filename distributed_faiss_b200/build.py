@@ -66,6 +66,18 @@ def build(force: bool = False, verbose: bool = False) -> str:
     want = source_hash()
     if not force and embedded_hash() == want:
         return LIB
+    # one builder at a time (several ranks of one job may find the same stale binary)
+    import fcntl
+
+    os.makedirs(OBJ, exist_ok=True)
+    with open(os.path.join(OBJ, ".lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        if not force and embedded_hash() == want:   # another process built it while we waited
+            return LIB
+        return _build_locked(want, verbose)
+
+
+def _build_locked(want: str, verbose: bool) -> str:
     if not os.path.exists(NVCC):
         raise RuntimeError(f"nvcc not found at {NVCC}; libdfx.so cannot be built")
     os.makedirs(OBJ, exist_ok=True)
@@ -86,11 +98,13 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
         objs = list(ex.map(compile_one, SOURCES))
-    cmd = [NVCC, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a",
+    tmp = LIB + ".tmp"
+    cmd = [NVCC, "-shared", "-o", tmp, *objs, "-gencode", "arch=compute_100a,code=sm_100a",
            "-ccbin", "/usr/bin/g++", "-lcudart"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    os.replace(tmp, LIB)   # readers see the old or the new library, never a partial one
     if embedded_hash() != want:
         raise RuntimeError("libdfx.so was built but does not carry the expected source hash")
     return LIB

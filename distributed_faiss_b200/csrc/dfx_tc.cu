@@ -939,15 +939,21 @@ __global__ void assign_resolve_kernel(const float* __restrict__ qnorm2, const in
 // rerank_kernel), selected by the radix select of dfx_select.cuh.  Rare by construction (more than
 // `margin` group minima within the tolerance: duplicate centroids / duplicate rows); slow but exact.
 struct ExactLoader {
-    const float* Q;
+    const float* q;  // the row's query, staged in shared memory by the kernel
     const float* X;
     const float* xnorm;
-    int d, metric;
-    __device__ __forceinline__ uint64_t operator()(int64_t row, int e) const {
-        const float* q = Q + row * d;
+    int d, metric;   // d % 4 == 0 (the tensor-core path requires d % 64 == 0)
+    __device__ __forceinline__ uint64_t operator()(int64_t /*row*/, int e) const {
         const float* x = X + (int64_t)e * d;
         float acc = 0.f;
-        for (int k = 0; k < d; k++) acc = __fmaf_rn(q[k], x[k], acc);
+#pragma unroll 8
+        for (int k = 0; k < d; k += 4) {  // 8 row loads in flight, the canonical seq-k FMA chain
+            const float4 xv = *reinterpret_cast<const float4*>(x + k);
+            acc = __fmaf_rn(q[k + 0], xv.x, acc);
+            acc = __fmaf_rn(q[k + 1], xv.y, acc);
+            acc = __fmaf_rn(q[k + 2], xv.z, acc);
+            acc = __fmaf_rn(q[k + 3], xv.w, acc);
+        }
         const float v = (metric == DFX_METRIC_IP) ? -acc : __fmaf_rn(-2.f, acc, xnorm[e]);
         return dfx_comp(v, (uint32_t)e);
     }
@@ -964,13 +970,20 @@ struct ExactWriter {  // mode 2: keys[row][K]; mode 1: assign[row]; mode 0: out[
         else out[row * K + j] = c;
     }
 };
+// dynamic smem: P composites, then the row's query (d floats)
 __global__ void __launch_bounds__(256)
-tc_exact_rows_kernel(ExactLoader ld, ExactWriter wr, const int32_t* __restrict__ ovf, int n, int k, int P,
-                     int sort_cap) {
+tc_exact_rows_kernel(const float* __restrict__ Q, ExactLoader ld, ExactWriter wr, const int32_t* __restrict__ ovf,
+                     int n, int k, int P, int sort_cap) {
     DFX_DYN_SMEM(unsigned char, ex_smem, 16);
+    uint64_t* s_out = reinterpret_cast<uint64_t*>(ex_smem);
+    float* s_q = reinterpret_cast<float*>(ex_smem + (size_t)P * 8);
+    ld.q = s_q;
     const int count = ovf[0];
     for (int b = blockIdx.x; b < count; b += gridDim.x) {
-        dfx_select_row<256>(ld, wr, (int64_t)ovf[2 + b], n, k, P, sort_cap, reinterpret_cast<uint64_t*>(ex_smem));
+        const int64_t row = ovf[2 + b];
+        for (int i = threadIdx.x; i < ld.d; i += 256) s_q[i] = Q[row * ld.d + i];
+        __syncthreads();
+        dfx_select_row<256>(ld, wr, row, n, k, P, sort_cap, s_out);
         __syncthreads();
     }
 }
@@ -982,10 +995,12 @@ static void launch_exact_rows(const float* Q, const float* X, const float* xnorm
     const int sort_cap = 2048, n = (int)ncols;
     const int base = (n <= sort_cap) ? (n > K ? n : K) : K;
     const int P = dfx_next_pow2(base < 2 ? 2 : base);
-    ExactLoader ld{Q, X, xnorm, d, metric};
+    ExactLoader ld{nullptr, X, xnorm, d, metric};
     ExactWriter wr{mode, K, keys, assign, out};
     const unsigned grid = (unsigned)std::min<int64_t>(nrows, 2 * 148);
-    DFX_LAUNCH(tc_exact_rows_kernel, grid, 256, (size_t)P * 8, st, ld, wr, ovf, n, K, P, sort_cap);
+    const size_t smem = (size_t)P * 8 + (size_t)d * 4;
+    DFX_CUDA(cudaFuncSetAttribute(tc_exact_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    DFX_LAUNCH(tc_exact_rows_kernel, grid, 256, smem, st, Q, ld, wr, ovf, n, K, P, sort_cap);
 }
 
 __global__ void max_reduce_kernel(const float* __restrict__ x, int64_t n, float* __restrict__ out) {
@@ -1248,8 +1263,10 @@ void dfx_tc_coarse_search(dfx_index* idx, const float* d_x, int64_t nq, int npro
     const int metric = idx->cfg.metric;
     const int64_t nl_pad = dfx_ceil_div(nlist, tc::TILE) * tc::TILE;
     const int ng = (int)(nl_pad / 32);
+    // groups kept per query: nprobe + 8; with few groups in all (nlist <= 2048) every one is kept,
+    // so that no row can overflow (at d = 768, nprobe 32 of 64 groups, most rows did)
     int G = nprobe + 8;
-    if (G > ng) G = ng;
+    if (G > ng || ng <= 64) G = ng;
     const int64_t QC = std::max<int64_t>(tc::TILE, ((64ll << 20) / ((int64_t)ng * 4)) / tc::TILE * tc::TILE);
     const int64_t qmax = std::min<int64_t>(nq, QC);
     idx->tc_gmin.reserve((size_t)qmax * ng * 4);
@@ -1278,6 +1295,8 @@ void dfx_tc_coarse_search(dfx_index* idx, const float* d_x, int64_t nq, int npro
         const int P_cand = dfx_next_pow2(G * 32 < 32 ? 32 : G * 32);
         if (nprobe <= 32 && G <= 64 && d % 4 == 0) {  // warp per query
             const size_t smem = (size_t)RR2_WARPS * ((d + 3) / 4 * 4) * 4 + (size_t)RR2_WARPS * G * 32 * 4;
+            if (smem > 48 * 1024)
+                DFX_CUDA(cudaFuncSetAttribute(rerank2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             DFX_LAUNCH(rerank2_kernel, (unsigned)dfx_ceil_div(qc, RR2_WARPS), RR2_WARPS * 32, smem, st, xq, d, cent,
                        cnorm, nlist, metric, groups, G, nprobe, gmin, gmin2, gargc, ng, idx->tc_cmax2, tol, qc, kq, ovf);
         } else if (P_cand <= 4096) {  // fused: candidates never leave the SM
