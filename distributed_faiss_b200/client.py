@@ -251,7 +251,17 @@ class IndexClient:
             conn.close()
 
     # ------------------------------------------------------------ the hot path
+    MAX_TOPK = 1024   # per-query results the engine selects for the IVF kinds (flat: 4096); DESIGN.md §7
+
+    def _check_topk(self, topk: int):
+        """the reference passes any k to faiss; here the limit is the engine's -- say so on the
+        client instead of surfacing it as a ServerException from every shard"""
+        if not 1 <= int(topk) <= 4096:
+            raise ValueError(f"topk={topk}: this engine returns 1..{self.MAX_TOPK} results per query for the IVF "
+                             "builders (4096 for 'flat'); search_with_filter over-fetches 3x")
+
     def search(self, query, topk: int, index_id: str, return_embeddings: bool = False) -> Tuple[np.ndarray, List]:
+        self._check_topk(topk)
         maximize_metric: bool = self.cfg.metric == "dot"
         if self.plane is not None:
             return self._search_plane(query, topk, index_id, return_embeddings, maximize_metric)
@@ -264,6 +274,7 @@ class IndexClient:
         (client.py:213-263).  Returns per-query lists (possibly shorter than top_k)."""
         if filter_pos < 0:
             return self.search(query, top_k, index_id)
+        self._check_topk(3 * top_k)
         if self.plane is not None:
             return self._search_with_filter_plane(query, top_k, index_id, filter_pos, filter_value)
         scores, meta = self.search(query, 3 * top_k, index_id)

@@ -367,6 +367,7 @@ class ShardGroup:
 OP_STOP, OP_SEARCH, OP_TIMER_START, OP_TIMER_STOP = 0, 1, 2, 3
 F_MAXIMIZE, F_EMBS, F_INT_META, F_FILTER, F_HAVE_QUERY = 1, 2, 4, 8, 16
 HDR_WORDS = 32                      # int64 words: 8 scalars + 128 bytes of index id + spare
+HDR_RING = 64                       # pinned header buffers in flight (see SearchPlane.__init__)
 ST_OK, ST_NOT_TRAINED, ST_META_KIND, ST_NO_INDEX, ST_ERROR = 0, 1, 2, 3, 4
 
 _plane_lock = threading.Lock()
@@ -404,7 +405,12 @@ class SearchPlane:
             assert s.rank == self.rank * self.S_loc + j, "server ranks must be rank-major over the plane"
         self._groups = {}
         self._lock = threading.Lock()          # one search at a time through the plane
-        self._hdr_pin = self._pin((HDR_WORDS,), torch.int64)
+        # headers go out through a RING of pinned buffers: the host-to-device copy of a header is
+        # asynchronous, and a caller that enqueues device-resident searches back to back (no sync)
+        # must not overwrite a header the copy engine has not read yet
+        self._hdr_ring = [self._pin((HDR_WORDS,), torch.int64) for _ in range(HDR_RING)]
+        self._hdr_done = [None] * HDR_RING
+        self._hdr_next = 0
         self._pin_q = None
         self._pin_out = None
         self._t0 = None
@@ -448,8 +454,17 @@ class SearchPlane:
         h[8:24].view(np.uint8)[:len(raw)] = np.frombuffer(raw, dtype=np.uint8)
         h[24] = len(blob)
         if self.world > 1:
-            self._hdr_pin.numpy()[...] = h
-            h_dev = self._hdr_pin.to(self.device, non_blocking=True)
+            slot = self._hdr_next
+            self._hdr_next = (slot + 1) % HDR_RING
+            if self._hdr_done[slot] is not None:
+                self._hdr_done[slot].synchronize()   # the copy that last used this buffer has read it
+            pin = self._hdr_ring[slot]
+            pin.numpy()[...] = h
+            h_dev = pin.to(self.device, non_blocking=True)
+            if self.device.type == "cuda":
+                ev = torch.cuda.Event()
+                ev.record()
+                self._hdr_done[slot] = ev
             dist.broadcast(h_dev, src=0, group=self.group)
             if blob:
                 b_dev = torch.from_numpy(np.frombuffer(blob, dtype=np.uint8).copy()).to(self.device)

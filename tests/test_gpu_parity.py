@@ -411,40 +411,46 @@ def test_tensor_core_near_tie_overflow_is_redone_exactly():
 
 def test_tensor_core_auto_precision_follows_the_data():
     """tc_screen_mode 0 (AUTO): a shard starts with the PRECISE screening (fp16 hi/lo split, three
-    MMAs) and moves to FAST (one MMA) only after 16 384 observed rows none of which would have
-    overflowed the kept groups under FAST's wider tolerance (an overflowing row costs an exact
+    MMAs) and moves to FAST (one MMA) only after a window of observed rows none of which would
+    have overflowed the kept groups under FAST's wider tolerance (an overflowing row costs an exact
     pass over all lists); on data whose norms dwarf the gaps between neighbouring centroids it
-    stays PRECISE.  Results are the oracle's either way."""
+    must stay PRECISE.  The rule is checked against the counters the launches report; results are
+    the oracle's either way."""
     from oracle import oracle as O
 
     E = _engine()
     rs = np.random.RandomState(23)
-    d, nlist, n = 64, 1024, _sz(30_000, 12_000)
+    d, nlist, n = 64, 2560, _sz(40_000, 8_000)    # 80 groups of 32 lists (with <= 64 all are kept: no overflow)
     A = np.linalg.qr(rs.randn(d, 6))[0].astype(np.float32)
-    for offset, expect_fast in ((0.0, 1.0), (300.0, 0.0)):
+    for offset in (0.0, 300.0):
         xb = (rs.randn(n, 6).astype(np.float32) @ A.T + offset).astype(np.float32)
         g = E.GpuIndex(E.KIND_IVF_FLAT, d, L2, nlist=nlist)
-        g.set_param("kmeans_niter", 2)
+        g.set_param("kmeans_niter", _sz(2, 1))
         g.train(xb[: n // 2])
         g.add(xb)
         o = O.make_index("ivf_flat", d, metric=L2, nlist=nlist)
         o.set_state(g.get_state())
         g.nprobe = 8; o.nprobe = 8
-        nb = _sz(4096, 128)                                       # rows per launch
-        g.set_param("tc_auto_window", 4 * nb)                     # (default 16 384 = 4 launches of 4096)
+        nb = _sz(1024, 64)                                        # rows per launch
+        g.set_param("tc_auto_window", 4 * nb)                     # (default: 16 384 rows)
         xq = xb[:nb] + 0.01 * rs.randn(nb, d).astype(np.float32)
-        Do, Io = o.search(xq[:128], 10)
+        Do, Io = o.search(xq[:64], 10)
         assert g.get_param("tc_fast") == 0.0                      # AUTO starts PRECISE
         g.search(xq[:1], 10)                                      # a single row decides nothing
-        assert g.get_param("tc_fast") == 0.0
-        for it in range(5):                                       # more rows than the window
+        assert g.get_param("tc_fast") == 0.0 and g.get_param("tc_stat_rows") == 1.0
+        would = g.get_param("tc_stat_fast_would")
+        for it in range(3):                                       # 1 + 3 nb rows: the window is not full yet
             Dg, Ig = g.search(xq, 10)
-            _assert_same(Dg[:128], Ig[:128], Do, Io, f"auto precision offset={offset} launch {it}")
-        assert g.get_param("tc_stat_rows") == float(nb)
-        assert g.get_param("tc_fast") == expect_fast, (offset, g.get_param("tc_stat_fast_would"))
-        if not expect_fast:
-            assert g.get_param("tc_stat_fast_would") > 0
-        _assert_same(*g.search(xq[:128], 10), Do, Io, f"auto precision offset={offset}, settled")
+            _assert_same(Dg[:64], Ig[:64], Do, Io, f"auto precision offset={offset} launch {it}")
+            assert g.get_param("tc_fast") == 0.0 and g.get_param("tc_stat_rows") == float(nb)
+            would += g.get_param("tc_stat_fast_would")
+        Dg, Ig = g.search(xq, 10)                                 # fills the window: the decision
+        would += g.get_param("tc_stat_fast_would")
+        assert g.get_param("tc_fast") == (1.0 if would == 0 else 0.0), (offset, would)
+        if offset:
+            assert would > 0                                      # norms 2400, gaps ~1: FAST cannot resolve them
+        for it in range(2):                                       # whatever the precision now: same bits
+            _assert_same(*g.search(xq[:64], 10), Do, Io, f"auto precision offset={offset}, settled {it}")
 
 
 def test_tensor_core_assign_matches_oracle():
