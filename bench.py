@@ -558,8 +558,8 @@ def main():
     hb = batches[0][:64].cpu().numpy()
     Dp, Mp = client.search(hb, K, "bench")
     client.detach_plane()
-    Ds, Ms = client.search(hb, K, "bench")
-    client.plane = plane
+    Ds, Ms = client.search(hb, K, "bench")   # (at N > 1 the other ranks' server threads answer while
+    client.plane = plane                      #  their main threads wait in plane.serve_forever())
     plane_equals_socket = bool(np.array_equal(Dp, Ds) and Mp == Ms)
 
     sweep, sweep_e2e = {}, {}

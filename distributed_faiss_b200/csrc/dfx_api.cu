@@ -101,6 +101,7 @@ void dfx_destroy(dfx_index* idx) {
             cudaEventDestroy(e.second);
         }
         if (idx->tc_stat_ev) cudaEventDestroy(idx->tc_stat_ev);
+        if (idx->dev_done) cudaEventDestroy(idx->dev_done);
         if (idx->tc_stat_h) cudaFreeHost(idx->tc_stat_h);
         delete idx;
     }

@@ -87,9 +87,26 @@ struct dfx_index {
     // a non-blocking stream) wait for it first so that the two never race
     cudaStream_t last_dev_stream = nullptr;
     bool dev_work_pending = false;
+    // An EVENT after the call's own work, not the stream: the caller may queue unrelated work
+    // behind it on the same stream -- the search plane queues the wait for the NEXT header
+    // broadcast, which only completes when the client rank sends one, and a socket search served
+    // meanwhile by another thread of the same process must not wait for that (it deadlocked the
+    // 2-GPU bench: rank 0 waited for the socket reply, rank 1's reply for rank 0's next header).
+    cudaEvent_t dev_done = nullptr;
+    bool dev_done_recorded = false;
     void note_dev(cudaStream_t st) {
         last_dev_stream = st;
         dev_work_pending = true;
+        dev_done_recorded = false;
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(st, &cs) != cudaSuccess) cudaGetLastError();
+        if (cs != cudaStreamCaptureStatusNone) return;  // inside a graph capture: the capturing caller orders its replays
+        if (!dev_done && cudaEventCreateWithFlags(&dev_done, cudaEventDisableTiming) != cudaSuccess) {
+            cudaGetLastError();
+            dev_done = nullptr;
+        }
+        if (dev_done && cudaEventRecord(dev_done, st) == cudaSuccess) dev_done_recorded = true;
+        else cudaGetLastError();
     }
     // a *_dev call on a different stream than the previous one: order them
     void join_dev_if_other(cudaStream_t st) {
@@ -97,7 +114,8 @@ struct dfx_index {
     }
     void join_dev() {
         if (dev_work_pending) {
-            cudaStreamSynchronize(last_dev_stream);
+            if (dev_done_recorded) cudaEventSynchronize(dev_done);
+            else cudaStreamSynchronize(last_dev_stream);
             dev_work_pending = false;
         }
     }

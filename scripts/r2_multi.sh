@@ -7,7 +7,7 @@ mkdir -p gpurun_out
 if [ "${WITH_TESTS:-0}" = "1" ]; then
   timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "tensor_core or flat" 2>&1 | tail -3 | tee gpurun_out/multi${N}_suite.log
 fi
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 \
+timeout ${BENCH_TIMEOUT:-360} python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 \
     bench.py --gpus $N --steps 20 --warmup 5 > gpurun_out/multi${N}_bench.json 2> gpurun_out/multi${N}_bench.err
 python - <<PY
 import json
