@@ -35,6 +35,13 @@ import pickle
 import threading
 from typing import List, Optional, Sequence
 
+# A process that serves the plane also answers control-plane and socket RPCs from other threads.
+# With CUDA's default LAZY module loading the first launch of any kernel needs a context-wide
+# synchronisation, which cannot complete while a NCCL kernel of this process waits for its peer
+# (every rank sitting in serve_forever() has one pending): load kernels eagerly.  Effective only
+# if set before the CUDA context exists (import this module before the first CUDA call).
+os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
+
 import numpy as np
 import torch
 import torch.distributed as dist
