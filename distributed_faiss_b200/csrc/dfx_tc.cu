@@ -155,8 +155,8 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
     return d;
 }
 
-// instruction descriptor: D=f32, A=B=f16 (format 0), both K-major, M=128, N=128
-static constexpr uint32_t TC_IDESC = (1u << 4) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+// instruction descriptor: D=f32, A=B=f16 (format 0), both K-major, M=128, N = 128 or 256
+static constexpr uint32_t tc_idesc(uint32_t n) { return (1u << 4) | ((n >> 3) << 17) | ((128u >> 4) << 24); }
 
 #endif  // !DFX_EMU
 
@@ -166,25 +166,33 @@ constexpr int TILE = 128;           // rows of A and of B per tile
 constexpr int KATOM = 64;           // fp16 elements per 128-byte swizzle row
 constexpr int ATOM_BYTES = TILE * KATOM * 2;  // 16 KB
 constexpr int THREADS = 192;        // TMA warp + MMA warp + 4 epilogue warps
-constexpr int TMEM_COLS = 256;      // two 128-column accumulator buffers
 constexpr int MAX_RESIDENT_KATOMS = 4;  // query tile resident in shared memory up to 4 atoms (64 KB): FAST d <= 256, PRECISE d <= 128
 // Screening precision (NPL = planes per operand):
 //   FAST    NPL 1: fp16(x s); one MMA per k-step; error <= |q||c| (2^-10 + 2^-13)
 //   PRECISE NPL 2: hi = fp16(x s), lo = fp16(x s - hi); q.c ~= qh.ch + ql.ch + qh.cl, three MMAs per
 //           k-step; error <= |q||c| 2^-17 (the dropped ql.cl term is 2^-22, hi + lo carries 22 bits)
 // shared-memory plan (offsets inside the 1024-aligned dynamic block)
-//   resident A (NPL x katoms <= 4): A = NPL x katoms x 16 KB, then a ring of B stages of 16 KB
-//                          (FAST, d <= 128: 4 stages, 97 KB, two CTAs per SM; PRECISE: 8 stages)
+//   resident A (NPL x katoms <= 4): A = NPL x katoms x 16 KB, then a ring of 4 B stages
+//                          (FAST: 16 KB stages, d <= 128: 97 KB, two CTAs per SM;
+//                           PRECISE: 32 KB stages = 256 centroids, 192 KB)
 //   streamed A (larger d): a ring of 6 stages of (A atom + B atom) = 32 KB
 struct Smem {
     static constexpr bool resident(int katoms, int npl) { return npl * katoms <= MAX_RESIDENT_KATOMS; }
-    static constexpr int nstage(bool res, int npl) { return res ? (npl == 1 ? 4 : 8) : 6; }
-    static constexpr int stage_bytes(bool res) { return res ? ATOM_BYTES : 2 * ATOM_BYTES; }
+    // tile width in centroids: resident PRECISE uses N = 256 (one B stage = two 16 KB atoms side by
+    // side): three SS-mode M = N = 128 MMAs per k-step read 24 KB per 192 cycles -- the SM's whole
+    // 128 B/clk, before the TMA fill -- while N = 256 re-uses each A read over twice the columns
+    // (36 KB per 384 cycles); everything else keeps N = 128 (two accumulators of N = 256 are all
+    // of TMEM, which excludes the two-CTAs-per-SM shape of FAST)
+    static constexpr int tile_n(bool res, int npl) { return (res && npl == 2) ? 256 : 128; }
+    static constexpr int nstage(bool res, int npl) { return res ? 4 : 6; }
+    static constexpr int stage_bytes(bool res, int npl) { return res ? (tile_n(res, npl) / TILE) * ATOM_BYTES : 2 * ATOM_BYTES; }
     static constexpr int RING(bool res, int katoms, int npl) { return res ? npl * katoms * ATOM_BYTES : 0; }
     static constexpr int BARS(bool res, int katoms, int npl) {
-        return RING(res, katoms, npl) + nstage(res, npl) * stage_bytes(res);
+        return RING(res, katoms, npl) + nstage(res, npl) * stage_bytes(res, npl);
     }
-    static constexpr int total(bool res, int katoms, int npl) { return BARS(res, katoms, npl) + 512 + 2 * TILE * 4; }
+    static constexpr int total(bool res, int katoms, int npl) {
+        return BARS(res, katoms, npl) + 512 + 2 * tile_n(res, npl) * 4;
+    }
 };
 }  // namespace tc
 
@@ -302,7 +310,10 @@ tc_coarse_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     constexpr bool RES = KT != 0;
     const int KATOMS = KT ? KT : katoms_rt;
     constexpr int NSTAGE = Smem::nstage(RES, NPL);
-    constexpr int STAGE_BYTES = Smem::stage_bytes(RES);
+    constexpr int STAGE_BYTES = Smem::stage_bytes(RES, NPL);
+    constexpr int TN = Smem::tile_n(RES, NPL);   // centroids per tile
+    constexpr int TMEM_COLS = 2 * TN;            // two accumulator buffers
+    constexpr uint32_t IDESC = tc_idesc(TN);
     // operand pairs accumulated per k-atom: FAST (qh, ch); PRECISE (qh, ch), (ql, ch), (qh, cl)
     constexpr int NCOMBO = NPL == 1 ? 1 : 3;
     extern __shared__ unsigned char smem_raw_tc[];
@@ -317,11 +328,11 @@ tc_coarse_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     uint64_t* t_full = a_full + 1;         // [2]
     uint64_t* t_empty = t_full + 2;        // [2]
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(t_empty + 2);
-    float* s_cn = reinterpret_cast<float*>(smem + Smem::BARS(RES, KATOMS, NPL) + 512);  // [2][TILE]
+    float* s_cn = reinterpret_cast<float*>(smem + Smem::BARS(RES, KATOMS, NPL) + 512);  // [2][TN]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int qt = blockIdx.y;
-    const int ctiles = nl_pad / TILE;
+    const int ctiles = (nl_pad + TN - 1) / TN;  // (TN = 256: the last tile may be half outside; zero / masked)
     const int ct0 = blockIdx.x * ctiles_per_cta;
     const int ct1 = min(ctiles, ct0 + ctiles_per_cta);
     const int ntiles = ct1 - ct0;
@@ -360,7 +371,7 @@ tc_coarse_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             }
             int stage = 0, phase = 0;
             for (int t = 0; t < ntiles; t++) {
-                const int crow = (ct0 + t) * TILE;
+                const int crow = (ct0 + t) * TN;
                 // RES: c = B plane; streamed: c = combo
                 for (int c = 0; c < (RES ? NPL : NCOMBO); c++)
                 for (int ka = 0; ka < KATOMS; ka++) {
@@ -394,7 +405,7 @@ tc_coarse_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                 const int buf = t & 1;
                 mbar_wait(&t_empty[buf], ((t >> 1) & 1) ^ 1);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + buf * TILE;
+                const uint32_t d_tmem = tmem_base + buf * TN;
 #pragma unroll
                 for (int c = 0; c < (RES ? NPL : NCOMBO); c++)
 #pragma unroll
@@ -408,11 +419,11 @@ tc_coarse_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 #pragma unroll
                     for (int kk = 0; kk < KATOM / 16; kk++) {  // UMMA_K = 16 fp16 = 32 bytes
                         const uint64_t bd = make_kmajor_sw128_desc(b_addr + kk * 32);
-                        tc_mma_f16(d_tmem, make_kmajor_sw128_desc(ah_addr + kk * 32), bd, TC_IDESC,
+                        tc_mma_f16(d_tmem, make_kmajor_sw128_desc(ah_addr + kk * 32), bd, IDESC,
                                    (c > 0 || ka > 0 || kk > 0) ? 1u : 0u);
                         // resident PRECISE: the hi-plane B stage also takes ql . ch
                         if (RES && NPL == 2 && c == 0)
-                            tc_mma_f16(d_tmem, make_kmajor_sw128_desc(al_addr + kk * 32), bd, TC_IDESC, 1u);
+                            tc_mma_f16(d_tmem, make_kmajor_sw128_desc(al_addr + kk * 32), bd, IDESC, 1u);
                     }
                     tc_commit(&empty[stage]);  // frees the stage once these MMAs have read it
                     if (++stage == NSTAGE) {
@@ -440,39 +451,46 @@ tc_coarse_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         asm volatile("mov.u32 %0, 0xffffffe0;" : "=r"(idx_mask));
         for (int t = 0; t < ntiles; t++) {
             const int buf = t & 1;
-            const int col0 = (ct0 + t) * TILE;
-            {
-                const int c = col0 + et;
+            const int col0 = (ct0 + t) * TN;
+#pragma unroll
+            for (int e = et; e < TN; e += 128) {
+                const int c = col0 + e;
                 float cn = 0.f;
                 if (METRIC == DFX_METRIC_L2 && c < nlist) cn = cnorm[c];
-                s_cn[buf * TILE + et] = (c < nlist) ? cn : big;
+                s_cn[buf * TN + e] = (c < nlist) ? cn : big;
             }
             asm volatile("bar.sync 1, 128;" ::: "memory");
             mbar_wait(&t_full[buf], (t >> 1) & 1);
             tc_fence_after();
-            float gm[4], gm2[4];
-            uint32_t ga = 0;
 #pragma unroll
-            for (int ch = 0; ch < 4; ch++) {
-                uint32_t r[32];
-                tc_ld32(tmem_base + buf * TILE + ch * 32 + ((uint32_t)(quad * 32) << 16), r);
-                float m1 = big, m2 = big;
-                tc_two_smallest(r, s_cn + buf * TILE + ch * 32, mult, idx_mask, m1, m2,
-                                std::make_integer_sequence<int, 16>{});
-                gm[ch] = m1;
-                gm2[ch] = m2;
-                ga |= (__float_as_uint(m1) & 31u) << (8 * ch);
-            }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&t_empty[buf]);
-            if (grow < nq) {
-                const int64_t o = grow * ng + (col0 >> 5);
-                *reinterpret_cast<float4*>(gmin + o) = make_float4(gm[0], gm[1], gm[2], gm[3]);
-                *reinterpret_cast<float4*>(gmin2 + o) = make_float4(gm2[0], gm2[1], gm2[2], gm2[3]);
-                *reinterpret_cast<uint32_t*>(gargc + o) = ga;
-                // the tile's minimum: the first level of the group selection (topg_collect_kernel)
-                tmin[grow * (ng >> 2) + (col0 >> 7)] = fminf(fminf(gm[0], gm[1]), fminf(gm[2], gm[3]));
+            for (int half = 0; half < TN / 128; half++) {  // 128 columns = 4 groups = one selection tile
+                float gm[4], gm2[4];
+                uint32_t ga = 0;
+#pragma unroll
+                for (int ch = 0; ch < 4; ch++) {
+                    uint32_t r[32];
+                    tc_ld32(tmem_base + buf * TN + half * 128 + ch * 32 + ((uint32_t)(quad * 32) << 16), r);
+                    float m1 = big, m2 = big;
+                    tc_two_smallest(r, s_cn + buf * TN + half * 128 + ch * 32, mult, idx_mask, m1, m2,
+                                    std::make_integer_sequence<int, 16>{});
+                    gm[ch] = m1;
+                    gm2[ch] = m2;
+                    ga |= (__float_as_uint(m1) & 31u) << (8 * ch);
+                }
+                if (half == TN / 128 - 1) {  // the accumulator has been read: hand it back
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&t_empty[buf]);
+                }
+                const int colh = col0 + half * 128;
+                if (grow < nq && colh < nl_pad) {
+                    const int64_t o = grow * ng + (colh >> 5);
+                    *reinterpret_cast<float4*>(gmin + o) = make_float4(gm[0], gm[1], gm[2], gm[3]);
+                    *reinterpret_cast<float4*>(gmin2 + o) = make_float4(gm2[0], gm2[1], gm2[2], gm2[3]);
+                    *reinterpret_cast<uint32_t*>(gargc + o) = ga;
+                    // the tile's minimum: the first level of the group selection (topg_collect_kernel)
+                    tmin[grow * (ng >> 2) + (colh >> 7)] = fminf(fminf(gm[0], gm[1]), fminf(gm[2], gm[3]));
+                }
             }
         }
     }
@@ -1030,10 +1048,10 @@ static PFN_encodeTiled get_encode_fn() {
 }
 
 // fp16 matrix [rows, d] row-major, box = 128 rows x 64 columns, 128-byte swizzle
-static void make_tmap(CUtensorMap* tm, const void* base, int64_t rows, int d) {
+static void make_tmap(CUtensorMap* tm, const void* base, int64_t rows, int d, int box_rows = tc::TILE) {
     cuuint64_t gdim[2] = {(cuuint64_t)d, (cuuint64_t)rows};
     cuuint64_t gstr[1] = {(cuuint64_t)d * 2};
-    cuuint32_t box[2] = {(cuuint32_t)tc::KATOM, (cuuint32_t)tc::TILE};
+    cuuint32_t box[2] = {(cuuint32_t)tc::KATOM, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = get_encode_fn()(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), gdim, gstr, box,
                                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -1174,13 +1192,14 @@ static void tc_screen(dfx_index* idx, int d, const float* d_x, int64_t nq, const
                   nlist, nl_pad, d, npl, cnorm, metric, gmin, gmin2, gargc, tmin, ng);
     return;
 #else
-    CUtensorMap tmQ, tmC;
-    make_tmap(&tmQ, idx->tc_q.p, npl * nq_pad, d);
-    make_tmap(&tmC, table_h, npl * nl_pad, d);
-    const int qtiles = (int)(nq_pad / TILE), ctiles = (int)(nl_pad / TILE);
     const int katoms = d / KATOM;
     // resident only for the k-atom counts the kernel is instantiated for (1, 2, 4); others stream
     const bool res = Smem::resident(katoms, npl) && (katoms == 1 || katoms == 2 || katoms == 4);
+    const int tn = Smem::tile_n(res, npl);  // centroids per tile (and per TMA box of the table)
+    CUtensorMap tmQ, tmC;
+    make_tmap(&tmQ, idx->tc_q.p, npl * nq_pad, d);
+    make_tmap(&tmC, table_h, npl * nl_pad, d, tn);
+    const int qtiles = (int)(nq_pad / TILE), ctiles = (int)dfx_ceil_div(nl_pad, tn);
     const size_t smem = (size_t)Smem::total(res, katoms, npl) + 1024;
     const int slots = 148 * ((npl == 1 && smem <= 113 * 1024) ? 2 : 1);  // CTAs resident at once
     // split the centroid tiles so that the grid is close to a whole number of waves while every
