@@ -27,12 +27,6 @@ import time
 
 import numpy as np
 
-# every kernel loaded when its module is: with CUDA's default lazy loading the FIRST launch of a
-# kernel needs a context-wide synchronisation, which cannot complete while a NCCL kernel of the same
-# process waits for its peer (a rank sitting in SearchPlane.serve_forever() that also answers a
-# socket search with a not-yet-used kernel: the 2-GPU run of round 2 hung exactly there)
-os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
-
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 # stdout carries exactly ONE JSON line: keep NCCL's banner / debug output on stderr
@@ -561,10 +555,13 @@ def main():
     log(f"e2e done: {ms_e2e / args.steps:.3f} ms/step")
 
     # the same client through the reference's socket fan-out returns the same answer
-    # (at N = 1, where all 8 servers live in this process; at N > 1 the socket path would be served
-    # by threads of processes whose main thread waits in a NCCL broadcast -- see the note on
-    # CUDA_MODULE_LOADING above; tests/test_plane.py covers plane == socket at world size 2 on gloo,
-    # DFX_BENCH_SOCKET_CHECK=1 forces the check here)
+    # (at N = 1, where all 8 servers live in this process.  At N > 1 the socket path would be served
+    # by threads of processes whose main thread waits in a NCCL broadcast: the first launch of a
+    # not-yet-used kernel there needs a context-wide synchronisation under CUDA's lazy module
+    # loading, which cannot complete while that NCCL kernel waits for its peer -- the 2-GPU run of
+    # round 2 hung exactly there.  CUDA_MODULE_LOADING=EAGER avoids it at the price of minutes of
+    # start-up (every torch kernel is loaded); tests/test_plane.py covers plane == socket at world
+    # size 2 on gloo, DFX_BENCH_SOCKET_CHECK=1 forces the check here.)
     plane_equals_socket = None
     if world == 1 or os.environ.get("DFX_BENCH_SOCKET_CHECK") == "1":
         hb = batches[0][:64].cpu().numpy()

@@ -35,12 +35,14 @@ import pickle
 import threading
 from typing import List, Optional, Sequence
 
-# A process that serves the plane also answers control-plane and socket RPCs from other threads.
-# With CUDA's default LAZY module loading the first launch of any kernel needs a context-wide
-# synchronisation, which cannot complete while a NCCL kernel of this process waits for its peer
-# (every rank sitting in serve_forever() has one pending): load kernels eagerly.  Effective only
-# if set before the CUDA context exists (import this module before the first CUDA call).
-os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
+# NOTE for deployments that mix the two transports: a process that serves the plane also answers
+# control-plane and socket RPCs from other threads.  With CUDA's default LAZY module loading the
+# first launch of any kernel needs a context-wide synchronisation, which cannot complete while a
+# NCCL kernel of this process waits for its peer (every rank sitting in serve_forever() has one
+# pending).  Control-plane RPCs launch nothing; a socket SEARCH against such a process can hang on a
+# first-use kernel.  Either send searches through the plane only (what IndexClient does once
+# attached), or start the processes with CUDA_MODULE_LOADING=EAGER (minutes of extra start-up: every
+# torch kernel is loaded).
 
 import numpy as np
 import torch

@@ -327,7 +327,11 @@ def test_device_pointer_path_matches_host_path():
 
 # ------------------------------------------------------------------ K1 on tensor cores
 @pytest.mark.parametrize("kind,metric,d,M", [("ivf_pq", L2, 128, 32), ("ivf_flat", L2, 64, 0),
-                                             ("ivf_flat", IP, 128, 0), ("ivf_sq", L2, 128, 0)])
+                                             ("ivf_flat", IP, 128, 0), ("ivf_sq", L2, 128, 0),
+                                             # d = 256: query tile resident for FAST, streamed for PRECISE;
+                                             # d = 192 / 768 (config C4's dimension): k-atoms streamed
+                                             ("ivf_flat", L2, 256, 0), ("ivf_flat", IP, 192, 0),
+                                             ("ivf_sq", L2, 768, 0)])
 def test_tensor_core_coarse_quantizer_matches_oracle(kind, metric, d, M):
     """nlist >= 1024 and d a multiple of 64 route the coarse quantizer through tcgen05 (fp16
     screening: FAST one MMA per k-step, PRECISE hi/lo split, AUTO choosing between them from the
