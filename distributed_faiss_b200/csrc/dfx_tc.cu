@@ -503,36 +503,6 @@ tc_coarse_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 }
 #endif  // DFX_EMU
 
-// the G smallest group minima of a row, G <= 8: one warp per row, G rounds of warp arg-min
-template <int G>
-__global__ void topg_small_kernel(const float* __restrict__ gmin, int64_t nq, int ng,
-                                  int32_t* __restrict__ groups) {
-    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
-    if (row >= nq) return;
-    const float* g = gmin + row * ng;
-    uint64_t taken[G];
-#pragma unroll
-    for (int r = 0; r < G; r++) taken[r] = DFX_COMP_NONE;
-#pragma unroll
-    for (int r = 0; r < G; r++) {
-        uint64_t best = DFX_COMP_NONE;
-        const uint64_t prev = (r == 0) ? 0 : taken[r - 1];
-        for (int j = lane; j < ng; j += 32) {
-            uint64_t c = dfx_comp(g[j], (uint32_t)j);
-            // composites are unique: the r-th smallest is the smallest one above the (r-1)-th
-            if ((r == 0 || c > prev) && c < best) best = c;
-        }
-#pragma unroll
-        for (int off = 16; off >= 1; off >>= 1) {
-            uint64_t o = __shfl_xor_sync(0xffffffffu, best, off);
-            best = o < best ? o : best;
-        }
-        taken[r] = best;
-        if (lane == 0) groups[row * G + r] = (best == DFX_COMP_NONE) ? -1 : (int32_t)(uint32_t)best;
-    }
-}
-
 // Which columns of the selected groups can still matter?  With t = value of the nprobe-th
 // smallest group minimum and tol >= twice the screening error, every true top-nprobe centroid c
 // has approx(c) <= t + tol; inside its group it is either the arg-min column or has
