@@ -275,6 +275,11 @@ def test_round_robin_balance_and_misc(cluster):
         clients[0].sub_indexes[0].search("nope", rs.rand(1, d).astype(np.float32), 1, False)
     with pytest.raises(ServerException):
         clients[0].set_omp_num_threads(4)                              # no server implements it
+    # the engine's per-query result limit is reported by the client, not as 4 ServerExceptions
+    with pytest.raises(ValueError, match="topk"):
+        clients[1].search(rs.rand(2, d).astype(np.float32), 5000, index_id)
+    with pytest.raises(ValueError, match="topk"):
+        clients[1].search_with_filter(rs.rand(2, d).astype(np.float32), 2000, index_id, filter_pos=0, filter_value=1)
     assert clients[0].get_num_servers() == 4
     clients[0].save_index(index_id)
     clients[0].drop_index(index_id)
